@@ -1,0 +1,179 @@
+/*
+ * sdfmesh.h - C ABI of libsdfmesh.so, the B200-native (sm_100a) drop-in for the mesh-generation hot
+ * path of Meterius/bevy-signed-distance-mesh-generation.
+ *
+ * The reference has no host-side C ABI: its Rust `CudaHandler` (src/cuda/mod.rs) loads PTX with cudarc
+ * and launches two `extern "C" __global__` kernels with by-value `#[repr(C)]` structs bindgen-generated
+ * from cuda/includes/bindings.h.  This header therefore declares
+ *   (1) the struct layouts of bindings.h, byte for byte (a Rust host can keep its generated types);
+ *   (2) one C entry point per `CudaHandler` method on the path (what a Rust `extern "C"` block binds
+ *       instead of cudarc launches) - see INTEGRATION.md for the Rust side;
+ *   (3) the device-resident fast path (`sdm_remesh`) and the shard entry points used for multi-GPU.
+ * The two reference kernel symbols themselves are also shipped with their original ABI in the compat
+ * module (csrc/compat_module.cu -> compute_mesh_generation.ptx/.cubin), see INTEGRATION.md.
+ *
+ * All functions return 0 on success or a non-zero SdmStatus; sdm_last_error() gives the message.
+ * Nothing here falls back to the CPU: without a CUDA device every compute entry point fails.
+ * A handle is not thread-safe (the reference's handler lives in a Bevy NonSend resource,
+ * src/renderer/mod.rs:230-235).  Calls are synchronous unless stated otherwise.
+ */
+#ifndef SDFMESH_H
+#define SDFMESH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants re-exported by the reference's bindgen step (src/cuda/mod.rs:8) ------------------- */
+#define SDM_BLOCK_SIZE 128                     /* bindings.h:7  BLOCK_SIZE */
+#define SDM_MESH_GENERATION_INIT_FACTOR 32     /* bindings.h:9  MESH_GENERATION_INIT_FACTOR */
+#define SDM_MESH_GENERATION_BB_SIZE 5.0f       /* bindings.h:10 MESH_GENERATION_BB_SIZE */
+
+/* ---- FFI PODs: identical layout to bindings.h:43-64 (checked by static_asserts in csrc) ---------- */
+typedef struct SdmPoint { float x, y, z; } SdmPoint;                        /* Point      12 B */
+typedef struct SdmVoxelField {                                              /* VoxelField 32 B */
+    SdmPoint voxel_size;        /* @0  */
+    SdmPoint* voxels;           /* @16 min-corners of the active voxels */
+    unsigned int voxel_count;   /* @24 */
+} SdmVoxelField;
+typedef struct SdmVertex { SdmPoint position; SdmPoint normal; } SdmVertex; /* Vertex     24 B */
+typedef struct SdmTriangle { SdmVertex vertices[3]; } SdmTriangle;          /* Triangle   72 B */
+
+typedef enum SdmStatus {
+    SDM_OK = 0,
+    SDM_ERR_CUDA = 1,          /* a CUDA runtime call failed (message has the cudaError string) */
+    SDM_ERR_INVALID = 2,       /* bad argument */
+    SDM_ERR_NO_DEVICE = 3,     /* no usable CUDA device: there is no CPU fallback */
+    SDM_ERR_CAPACITY = 4,      /* a device buffer would exceed the configured limit */
+    SDM_ERR_STATE = 5          /* call order violated (e.g. mesh before a field exists) */
+} SdmStatus;
+
+/* ---- scene description ----------------------------------------------------------------------------
+ * The reference hard-codes one scene, sd_obj (cuda/modules/common.cu:222-226).  Here a scene is a
+ * left fold over a primitive table, evaluated in index order:
+ *     acc = FLT_MAX;  for i in 0..count:  acc = fold_i(acc, d_i(p))
+ * with fold = min (signed_distance.cu:109 pattern) or smooth_min(acc, d, k) (signed_distance.cu:20-23).
+ * Primitive distances are the reference's forms:
+ *   SPHERE        length(p - a) - radius                      (common.cu:224, signed_distance.cu:82-84)
+ *   BOX           sd_box(p, bp=a, bs=b)                       (signed_distance.cu:86-91)
+ *   CAPSULE       sd_line(p, b0=a, b1=b) - radius             (signed_distance.cu:77-80, :109)
+ *   BOX_SKELETON  sd_box_skeleton(p, bp=a, bs=b, lw=radius)   (signed_distance.cu:93-113, incl. its
+ *                 `bs[(dir+1)%2]` indexing); must use fold=min unless it is primitive 0
+ *   MANDELBULB    sd_mandelbulb(p / radius, 0) * radius       (signed_distance.cu:29-57; radius=0.4
+ *                 gives sd_unit_mandelbulb)
+ * sd_obj is { BOX_SKELETON(a=0, b=(3,1,.5), radius=.1, min), SPHERE(a=0, radius=1, smooth_min k=.5) }
+ * and is what sdm_scene_default() returns / what a fresh handle uses.
+ */
+typedef enum SdmPrimKind {
+    SDM_PRIM_SPHERE = 0, SDM_PRIM_BOX = 1, SDM_PRIM_CAPSULE = 2, SDM_PRIM_BOX_SKELETON = 3, SDM_PRIM_MANDELBULB = 4
+} SdmPrimKind;
+typedef enum SdmFoldOp { SDM_FOLD_MIN = 0, SDM_FOLD_SMOOTH_MIN = 1 } SdmFoldOp;
+
+typedef struct SdmPrimitive {      /* 40 B */
+    uint32_t kind;                 /* SdmPrimKind */
+    uint32_t fold;                 /* SdmFoldOp */
+    float k;                       /* smooth-min k (ignored for min) */
+    float radius;
+    float a[3];
+    float b[3];
+} SdmPrimitive;
+
+/* Grid parameters; the reference compiles these in (bindings.h:9-10). */
+typedef struct SdmParams {
+    float bb_size;                 /* cube edge; level-0 grid spans [-bb/2, bb/2)^3 */
+    uint32_t init_factor;          /* level-0 voxels per axis */
+    uint32_t levels;               /* refine steps performed by sdm_remesh */
+} SdmParams;
+
+/* Indexed mesh in the layout Bevy consumes (src/renderer/mod.rs:110-128): Float32x3 positions,
+ * Float32x3 normals, u32 triangle-list indices, in the reference's weld order (src/cuda/mod.rs:263-296). */
+typedef struct SdmMesh {
+    float* positions;              /* vertex_count * 3 */
+    float* normals;                /* vertex_count * 3 */
+    uint32_t* indices;             /* triangle_count * 3 */
+    uint32_t vertex_count;
+    uint32_t triangle_count;
+    int32_t on_device;             /* 1: pointers are device memory owned by the handle */
+    int32_t reserved;
+} SdmMesh;
+
+typedef struct SdmHandle SdmHandle;
+
+/* ---- lifecycle (CudaHandler::new, src/cuda/mod.rs:49-103) --------------------------------------- */
+int sdm_create(int device_ordinal, SdmHandle** out_handle);
+void sdm_destroy(SdmHandle* h);
+const char* sdm_last_error(void);
+const char* sdm_version(void);
+
+/* ---- scene ------------------------------------------------------------------------------------- */
+/* Writes the two primitives of the reference's sd_obj into out[0..1]; returns the count (2). */
+uint32_t sdm_scene_default(SdmPrimitive* out, uint32_t capacity);
+/* Compiles (segment set-up etc., with the reference's own operation order) and uploads the table. */
+int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count);
+/* Scene SDF at arbitrary host points (n*3 floats in, n floats out) - used by the parity tests. */
+int sdm_eval_sdf(SdmHandle* h, const float* points, uint32_t n, float* out_sd);
+/* empirical_normal / closest_surface_point (signed_distance.cu:181-202, :227-240) at host points. */
+int sdm_eval_normal(SdmHandle* h, const float* points, uint32_t n, float* out_normals);
+int sdm_eval_project(SdmHandle* h, const float* points, uint32_t n, float* out_points, uint32_t* out_iters);
+
+/* ---- the CudaHandler surface, host buffers in and out (drop-in semantics) ------------------------ */
+/* create_cuda_voxel_field (src/cuda/mod.rs:105-122).  params==NULL -> the reference's 32 / 5.0.
+ * The list is malloc'd by the library; release with sdm_voxel_field_free. */
+int sdm_create_voxel_field(const SdmParams* params, SdmVoxelField* out_field);
+void sdm_voxel_field_free(SdmVoxelField* field);
+/* refine_voxel_field (src/cuda/mod.rs:124-202): the host list is replaced by the stably compacted
+ * surviving children and voxel_size is halved.  Empty input is a no-op, as in the reference (:137). */
+int sdm_refine_voxel_field(SdmHandle* h, SdmVoxelField* field);
+/* voxel_field_to_mesh (src/cuda/mod.rs:204-346): welded indexed mesh in host memory owned by the
+ * library (release with sdm_mesh_free).  Empty input gives an empty mesh (:327-345). */
+int sdm_voxel_field_to_mesh(SdmHandle* h, const SdmVoxelField* field, SdmMesh* out_mesh);
+void sdm_mesh_free(SdmMesh* mesh);
+
+/* ---- device-resident path (nothing crosses PCIe between stages) ---------------------------------- */
+/* Level-0 field on the device (same contents as sdm_create_voxel_field). */
+int sdm_field_reset(SdmHandle* h, const SdmParams* params);
+/* Upload a host list as the current device field. */
+int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field);
+/* One subdivision level on the device field; *out_count (optional) receives the new voxel count. */
+int sdm_field_refine(SdmHandle* h, uint32_t* out_count);
+int sdm_field_count(SdmHandle* h, uint32_t* out_count, SdmPoint* out_voxel_size);
+/* Copies the current active list to host (capacity in voxels). */
+int sdm_field_download(SdmHandle* h, SdmPoint* out_voxels, uint32_t capacity);
+/* Per-voxel marching-cubes case index (marching_cubes.cu:19-23) of the current field, to host. */
+int sdm_field_cases(SdmHandle* h, uint8_t* out_cases, uint32_t capacity);
+/* Mesh of the current device field.  out_mesh->on_device=1; buffers stay valid until the next
+ * mesh/remesh call on this handle. */
+int sdm_field_to_mesh(SdmHandle* h, SdmMesh* out_mesh);
+/* Whole pipeline: level-0 field, params->levels refinements, mesh; device-resident result. */
+int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh);
+/* Copies a device-resident mesh into caller-provided host arrays (sizes from the SdmMesh counts). */
+int sdm_mesh_download(SdmHandle* h, const SdmMesh* device_mesh, float* positions, float* normals, uint32_t* indices);
+/* The reference's raw output format: 5 Triangle slots per voxel, NaN-padded
+ * (compute_mesh_generation.cu:64-120), to host (capacity in triangles, >= 5 * voxel_count). */
+int sdm_field_triangle_soup(SdmHandle* h, SdmTriangle* out_triangles, uint32_t capacity);
+
+/* ---- shards (multi-GPU: contiguous ranges of the level-`split_level` active list) --------------- */
+/* Restrict the device field to the [shard_index/shard_count) contiguous part of the current list,
+ * balanced by voxel count.  Global slot ids are preserved through sdm_shard_info so that per-shard
+ * meshes can be merged into exactly the single-GPU mesh. */
+int sdm_field_take_shard(SdmHandle* h, uint32_t shard_index, uint32_t shard_count);
+
+/* ---- counters for the bench ------------------------------------------------------------------------ */
+typedef struct SdmStats {
+    uint64_t kernel_launches;      /* kernels launched by this handle since creation */
+    uint64_t sdf_evals;            /* analytically counted SDF evaluations of the last remesh/mesh */
+    uint32_t level_counts[16];     /* active voxels after each level of the last remesh (index 0 = level 0) */
+    uint32_t unique_vertices;      /* distinct edge midpoints projected in the last mesh */
+    uint32_t raw_triangles;        /* triangles before the finite-vertex filter */
+    float last_gpu_ms;             /* CUDA-event time of the last remesh / mesh call on the handle's stream */
+    uint32_t reserved;
+} SdmStats;
+int sdm_get_stats(SdmHandle* h, SdmStats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFMESH_H */
