@@ -1,0 +1,774 @@
+// sdfmesh.cu - host side of libsdfmesh.so: the C ABI of include/sdfmesh.h over the kernels in sdm_kernels.cuh.
+//
+// Mirrors the reference's CudaHandler (src/cuda/mod.rs): grow-only device buffers owned by the handle
+// (DynamicCudaSlice, :10-23), one device, one stream.  Unlike the reference nothing is compacted or welded on
+// the host: the voxel list, the case indices, the vertex table and the index buffer all stay in HBM, and one
+// remesh is enqueued as a fixed sequence of persistent kernels that read their sizes from device memory; the
+// host synchronises once, at the end, to learn the counts.
+//
+// There is no CPU fallback: every compute entry point needs a CUDA device and fails with SDM_ERR_NO_DEVICE /
+// SDM_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sdm_kernels.cuh"
+
+static_assert(sizeof(SdmPoint) == 12 && alignof(SdmPoint) == 4, "Point layout (bindings.h:43-47)");
+static_assert(sizeof(SdmVoxelField) == 32 && offsetof(SdmVoxelField, voxels) == 16 && offsetof(SdmVoxelField, voxel_count) == 24,
+              "VoxelField layout (bindings.h:51-55)");
+static_assert(sizeof(SdmVertex) == 24, "Vertex layout (bindings.h:57-60)");
+static_assert(sizeof(SdmTriangle) == 72, "Triangle layout (bindings.h:62-64)");
+static_assert(sizeof(SdmPrimitive) == 40, "SdmPrimitive layout");
+
+using namespace sdm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CK(expr)                                                                                                 \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess)                                                                                   \
+            return fail(SDM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+    } while (0)
+
+template <class T> struct DevBuf {   // grow-only, like DynamicCudaSlice::get_or_alloc_sync (src/cuda/mod.rs:15-22)
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+uint32_t pow2_at_least(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t) std::min<uint64_t>(p, 1ull << 31);
+}
+
+// ---- scene compilation ---------------------------------------------------------------------------
+// Host float arithmetic here is compiled with -ffp-contract=off: each operation is one IEEE binary32
+// operation, the same the reference performs per call on the device (signed_distance.cu:78-79, 94-104).
+struct H3 { float x, y, z; };
+inline float& at(H3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+inline float at(const H3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+DevPrim make_capsule(H3 b0, H3 b1, float lw, uint32_t fold, float k) {
+    DevPrim d;
+    memset(&d, 0, sizeof(d));
+    const H3 ab { b1.x - b0.x, b1.y - b0.y, b1.z - b0.z };
+    const float len = sqrtf(ab.x * ab.x + ab.y * ab.y + ab.z * ab.z);   // length(b1 - b0)
+    const H3 bd { ab.x / len, ab.y / len, ab.z / len };                 // (b1 - b0) / len
+    d.v0[0] = b0.x; d.v0[1] = b0.y; d.v0[2] = b0.z;
+    d.v1[0] = bd.x; d.v1[1] = bd.y; d.v1[2] = bd.z;
+    d.v2[0] = b0.x + len * bd.x; d.v2[1] = b0.y + len * bd.y; d.v2[2] = b0.z + len * bd.z;   // bl + len * bd
+    d.s0 = lw; d.s1 = len; d.k = k;
+    d.kind = SDM_PRIM_CAPSULE; d.fold = fold;
+    return d;
+}
+
+int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>& blob, bool* has_mandelbulb) {
+    std::vector<DevPrim> dp;
+    *has_mandelbulb = false;
+    for (uint32_t i = 0; i < count; i++) {
+        const SdmPrimitive& q = prims[i];
+        if (q.fold != SDM_FOLD_MIN && q.fold != SDM_FOLD_SMOOTH_MIN) return fail(SDM_ERR_INVALID, "unknown fold op");
+        const H3 a { q.a[0], q.a[1], q.a[2] }, b { q.b[0], q.b[1], q.b[2] };
+        DevPrim d;
+        memset(&d, 0, sizeof(d));
+        d.kind = q.kind; d.fold = q.fold; d.k = q.k;
+        switch (q.kind) {
+            case SDM_PRIM_SPHERE:
+                d.v0[0] = a.x; d.v0[1] = a.y; d.v0[2] = a.z; d.s0 = q.radius;
+                dp.push_back(d);
+                break;
+            case SDM_PRIM_BOX:
+                d.v0[0] = a.x; d.v0[1] = a.y; d.v0[2] = a.z;
+                d.v1[0] = b.x / 2.0f; d.v1[1] = b.y / 2.0f; d.v1[2] = b.z / 2.0f;   // bs / 2.0f (signed_distance.cu:87)
+                dp.push_back(d);
+                break;
+            case SDM_PRIM_CAPSULE:
+                dp.push_back(make_capsule(a, b, q.radius, q.fold, q.k));
+                break;
+            case SDM_PRIM_BOX_SKELETON: {
+                // The skeleton's own fold is min from FLT_MAX (signed_distance.cu:95,109).  Flattening its 12 edges
+                // into the scene fold is exact when the scene fold at this point is min too, or when the skeleton
+                // is primitive 0 (fold(FLT_MAX, d) = d for both folds).
+                if (q.fold != SDM_FOLD_MIN && i != 0)
+                    return fail(SDM_ERR_INVALID, "BOX_SKELETON must use fold=min unless it is primitive 0");
+                const H3 bs = b;
+                const H3 bpl { a.x - bs.x / 2.0f, a.y - bs.y / 2.0f, a.z - bs.z / 2.0f };   // bp - bs / 2.0f
+                for (int dir = 0; dir < 3; dir++)
+                    for (int c0 = 0; c0 < 2; c0++)
+                        for (int c1 = 0; c1 < 2; c1++) {
+                            H3 m0 = bpl;
+                            at(m0, (dir + 1) % 3) += c0 ? at(bs, (dir + 1) % 2) : 0.0f;   // sic: % 2 (signed_distance.cu:101)
+                            at(m0, (dir + 2) % 3) += c1 ? at(bs, (dir + 2) % 3) : 0.0f;
+                            H3 m1 = m0;
+                            at(m1, dir) += at(bs, dir);
+                            dp.push_back(make_capsule(m0, m1, q.radius, SDM_FOLD_MIN, 0.0f));
+                        }
+            } break;
+            case SDM_PRIM_MANDELBULB:
+                d.s0 = q.radius;
+                *has_mandelbulb = true;
+                dp.push_back(d);
+                break;
+            default:
+                return fail(SDM_ERR_INVALID, "unknown primitive kind");
+        }
+    }
+    std::vector<DevRun> runs;
+    for (uint32_t i = 0; i < dp.size();) {
+        uint32_t j = i + 1;
+        while (j < dp.size() && dp[j].kind == dp[i].kind && dp[j].fold == dp[i].fold && j - i < 0xFFFFFFu) j++;
+        uint32_t flags = 0;
+        if (dp[i].kind == SDM_PRIM_CAPSULE && dp[i].fold == SDM_FOLD_MIN) {
+            bool same = true;
+            for (uint32_t q = i; q < j; q++) same = same && (memcmp(&dp[q].s0, &dp[i].s0, 4) == 0);
+            if (same) flags |= RUN_SHARED_RADIUS_MIN;
+        }
+        runs.push_back(DevRun { dp[i].kind, dp[i].fold, i, (j - i) | (flags << 24) });
+        i = j;
+    }
+    const size_t bytes = 16 + runs.size() * sizeof(DevRun) + dp.size() * sizeof(DevPrim);
+    blob.assign(bytes / 16, make_uint4(0, 0, 0, 0));
+    SceneHeader hdr { (uint32_t) dp.size(), (uint32_t) runs.size(), (uint32_t) bytes, 0 };
+    memcpy(blob.data(), &hdr, 16);
+    if (!runs.empty()) memcpy(blob.data() + 1, runs.data(), runs.size() * sizeof(DevRun));
+    if (!dp.empty()) memcpy(blob.data() + 1 + runs.size(), dp.data(), dp.size() * sizeof(DevPrim));
+    return SDM_OK;
+}
+
+}  // namespace
+
+struct SdmHandle {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // scene
+    DevBuf<uint4> scene;
+    uint32_t scene_bytes = 0;
+
+    // field (ping-pong lists) and its host-known description
+    DevBuf<float> vox[2];
+    int cur = 0;
+    int level = 0;              // index into DevState::level_count of the current list
+    float voxel_size[3] = { 0, 0, 0 };
+    bool have_field = false;
+    uint32_t cap_vox = 0;
+
+    // mesh intermediates
+    uint32_t cap_tris = 0, cap_uniq = 0, table_entries = 0;
+    DevBuf<uint8_t> cases;
+    DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix, out_idx;
+    DevBuf<float> ustart, upos, unrm, out_pos, out_nrm;
+    DevBuf<uint4> table1, table2;
+    DevBuf<uint64_t> tiles;
+    DevBuf<DevState> state;
+    DevState* host_state = nullptr;   // pinned
+    uint32_t epoch = 1;
+    bool mesh_valid = false;
+
+    // persistent grid sizes
+    int g_refine = 0, g_classify = 0, g_project = 0, g_normals = 0, g_orient = 0, g_light = 0;
+
+    SdmStats stats {};
+};
+
+namespace {
+
+size_t smem_for(const SdmHandle* h) { return (size_t) h->scene_bytes; }
+
+int configure_kernels(SdmHandle* h) {
+    const size_t smem = smem_for(h);
+    if (smem > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
+    struct K { const void* f; int threads; int* grid; };
+    const K ks[] = {
+        { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify, 256, &h->g_classify },
+        { (const void*) k_project, 128, &h->g_project }, { (const void*) k_vertex_normals, 128, &h->g_normals },
+        { (const void*) k_orient, 128, &h->g_orient },
+    };
+    for (const K& k : ks) {
+        CK(cudaFuncSetAttribute(k.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.f, k.threads, smem));
+        if (per_sm < 1) return fail(SDM_ERR_CUDA, "kernel does not fit on an SM");
+        *k.grid = per_sm * h->num_sms;
+    }
+    for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project })
+        CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
+    h->g_light = h->num_sms * 8;
+    return SDM_OK;
+}
+
+int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
+    if (cap_vox <= h->cap_vox) return SDM_OK;
+    // copy-preserving growth of the current list is not needed: callers re-create the field after growing
+    h->cap_vox = cap_vox;
+    h->cap_tris = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 3, 0x3FFFFFFFull);   // < 2^32 / 3 slots
+    h->cap_uniq = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 2, 0x7FFFFFFFull);
+    h->table_entries = pow2_at_least((uint64_t) h->cap_uniq * 2);
+    for (int i = 0; i < 2; i++) CK(h->vox[i].reserve((size_t) cap_vox * 3));
+    CK(h->cases.reserve(cap_vox));
+    CK(h->tri_off.reserve(cap_vox));
+    CK(h->slot_ref.reserve((size_t) h->cap_tris * 3));
+    CK(h->tri_uid.reserve((size_t) h->cap_tris * 3));
+    CK(h->out_idx.reserve((size_t) h->cap_tris * 3));
+    CK(h->first_bits.reserve(((size_t) h->cap_tris * 3 + 31) / 32 + 32));
+    CK(h->first_prefix.reserve(((size_t) h->cap_tris * 3 + 31) / 32 + 32));
+    CK(h->tri_valid_bits.reserve(((size_t) h->cap_tris + 31) / 32 + 32));
+    CK(h->tri_prefix.reserve(((size_t) h->cap_tris + 31) / 32 + 32));
+    CK(h->first_slot.reserve(h->cap_uniq));
+    CK(h->wref.reserve(h->cap_uniq));
+    CK(h->ustart.reserve((size_t) h->cap_uniq * 3));
+    CK(h->upos.reserve((size_t) h->cap_uniq * 3));
+    CK(h->unrm.reserve((size_t) h->cap_uniq * 3));
+    CK(h->out_pos.reserve((size_t) h->cap_uniq * 3));
+    CK(h->out_nrm.reserve((size_t) h->cap_uniq * 3));
+    CK(h->table1.reserve(h->table_entries));
+    CK(h->table2.reserve(h->table_entries));
+    const size_t max_tiles = std::max<size_t>(((size_t) h->cap_tris * 3 / 32 + 31) / 32, (size_t) cap_vox / 32) + 64;
+    const size_t old_tiles = h->tiles.n;
+    CK(h->tiles.reserve(max_tiles));
+    if (h->tiles.n != old_tiles) CK(cudaMemsetAsync(h->tiles.p, 0, h->tiles.n * sizeof(uint64_t), h->stream));
+    h->have_field = false;
+    h->mesh_valid = false;
+    return SDM_OK;
+}
+
+uint32_t next_epoch(SdmHandle* h) {
+    h->epoch++;
+    if (h->epoch >= (1u << 30)) {   // wrap: make every stale descriptor invalid again
+        cudaMemsetAsync(h->tiles.p, 0, h->tiles.n * sizeof(uint64_t), h->stream);
+        h->epoch = 1;
+    }
+    return h->epoch;
+}
+
+int reset_state(SdmHandle* h) {
+    CK(cudaMemsetAsync(h->state.p, 0, sizeof(DevState), h->stream));
+    return SDM_OK;
+}
+
+int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
+    const float size = p.bb_size / (float) p.init_factor;   // src/cuda/mod.rs:106
+    k_init_field<<<h->g_light, 256, 0, h->stream>>>(h->vox[0].p, h->state.p, p.bb_size, p.init_factor, size, h->cap_vox);
+    h->stats.kernel_launches++;
+    h->cur = 0; h->level = 0;
+    h->voxel_size[0] = h->voxel_size[1] = h->voxel_size[2] = size;
+    h->have_field = true;
+    h->mesh_valid = false;
+    return SDM_OK;
+}
+
+int enqueue_refine(SdmHandle* h) {
+    if (h->level >= 15) return fail(SDM_ERR_INVALID, "too many refinement levels (max 15)");
+    const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
+    k_refine<<<h->g_refine, 256, smem_for(h), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
+                                                           next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz);
+    h->stats.kernel_launches++;
+    h->cur ^= 1; h->level++;
+    h->voxel_size[0] = ox; h->voxel_size[1] = oy; h->voxel_size[2] = oz;
+    h->mesh_valid = false;
+    return SDM_OK;
+}
+
+int enqueue_mesh(SdmHandle* h) {
+    const float sx = h->voxel_size[0], sy = h->voxel_size[1], sz = h->voxel_size[2];
+    const float* vox = h->vox[h->cur].p;
+    const size_t smem = smem_for(h);
+    cudaStream_t s = h->stream;
+    const uint32_t mask = h->table_entries - 1;
+    // the mesh stage may be re-run on the same field: reset the mesh-stage counters and tickets only
+    CK(cudaMemsetAsync(&h->state.p->n_tris_raw, 0, offsetof(DevState, error_flags) - offsetof(DevState, n_tris_raw), s));   // not error_flags
+    CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY), s));
+    CK(cudaMemsetAsync(&h->state.p->newton_iters, 0, sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table_entries * 16, s));
+    CK(cudaMemsetAsync(h->table2.p, 0xFF, (size_t) h->table_entries * 16, s));
+    CK(cudaMemsetAsync(h->first_slot.p, 0xFF, (size_t) h->cap_uniq * 4, s));
+    CK(cudaMemsetAsync(h->first_bits.p, 0, h->first_bits.n * 4, s));
+    k_classify<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cases.p, h->tri_off.p,
+                                                 h->cap_tris, sx, sy, sz);
+    k_edges<<<h->g_light, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, mask, h->ustart.p, h->cap_uniq,
+                                        h->slot_ref.p, sx, sy, sz);
+    k_project<<<h->g_project, 128, smem, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq);
+    k_vertex_normals<<<h->g_normals, 128, smem, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq);
+    k_orient<<<h->g_orient, 128, smem, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
+                                             h->tri_valid_bits.p);
+    k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, mask, h->wref.p, h->cap_uniq);
+    k_weld_mark<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->cap_uniq);
+    k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_bits.p, h->first_prefix.p, 0, next_epoch(h), h->tiles.p);
+    k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_valid_bits.p, h->tri_prefix.p, 1, next_epoch(h), h->tiles.p);
+    k_emit_vertices<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
+                                                h->upos.p, h->unrm.p, h->out_pos.p, h->out_nrm.p, h->cap_uniq);
+    k_emit_indices<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
+                                               h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx.p);
+    h->stats.kernel_launches += 11;
+    CK(cudaGetLastError());
+    return SDM_OK;
+}
+
+// Copies DevState to the pinned host mirror and waits.  Returns the device-side error flags through *flags.
+int fetch_state(SdmHandle* h, uint32_t* flags) {
+    CK(cudaMemcpyAsync(h->host_state, h->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *flags = h->host_state->error_flags;
+    return SDM_OK;
+}
+
+void fill_stats(SdmHandle* h, bool meshed) {
+    const DevState& st = *h->host_state;
+    for (int i = 0; i < 16; i++) h->stats.level_counts[i] = st.level_count[i];
+    if (meshed) {
+        h->stats.unique_vertices = st.n_uniq;
+        h->stats.raw_triangles = st.n_tris_raw;
+    }
+    // analytic evaluation count: 27 per refined parent, 8 per meshed voxel, 13 per Newton iteration,
+    // 12 per vertex normal, 12 per triangle (centroid normal)
+    uint64_t evals = 0;
+    for (int l = 0; l < h->level; l++) evals += 27ull * st.level_count[l];
+    if (meshed) evals += 8ull * st.level_count[h->level] + 13ull * st.newton_iters + 12ull * st.n_uniq + 12ull * st.n_tris_raw;
+    h->stats.sdf_evals = evals;
+}
+
+void mesh_view(SdmHandle* h, SdmMesh* m) {
+    m->positions = h->out_pos.p;
+    m->normals = h->out_nrm.p;
+    m->indices = h->out_idx.p;
+    m->vertex_count = h->host_state->n_verts_out;
+    m->triangle_count = h->host_state->n_tris_out;
+    m->on_device = 1;
+    m->reserved = 0;
+}
+
+int check_params(const SdmParams& p) {
+    if (!(p.bb_size > 0.0f) || p.init_factor == 0 || p.init_factor > 2048 || p.levels > 15)
+        return fail(SDM_ERR_INVALID, "bad SdmParams");
+    return SDM_OK;
+}
+
+uint32_t grown(uint32_t cap) { return (uint32_t) std::min<uint64_t>((uint64_t) cap * 2, 1ull << 30); }
+
+}  // namespace
+
+extern "C" {
+
+const char* sdm_last_error(void) { return g_last_error.c_str(); }
+const char* sdm_version(void) { return "sdfmesh-b200 0.1 (sm_100a)"; }
+
+uint32_t sdm_scene_default(SdmPrimitive* out, uint32_t capacity) {
+    if (out && capacity >= 2) {
+        memset(out, 0, 2 * sizeof(SdmPrimitive));
+        // common.cu:222-226: smooth_min(sd_box_skeleton(p, vec3(0), vec3(3, 1, .5), .1), length(p) - 1, .5)
+        out[0].kind = SDM_PRIM_BOX_SKELETON; out[0].fold = SDM_FOLD_MIN; out[0].radius = 0.1f;
+        out[0].b[0] = 3.0f; out[0].b[1] = 1.0f; out[0].b[2] = 0.5f;
+        out[1].kind = SDM_PRIM_SPHERE; out[1].fold = SDM_FOLD_SMOOTH_MIN; out[1].k = 0.5f; out[1].radius = 1.0f;
+    }
+    return 2;
+}
+
+int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count) {
+    if (!h || (!prims && count)) return fail(SDM_ERR_INVALID, "null argument");
+    std::vector<uint4> blob;
+    bool mb = false;
+    int rc = compile_scene(prims, count, blob, &mb);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(h->scene.reserve(blob.size()));
+    CK(cudaMemcpyAsync(h->scene.p, blob.data(), blob.size() * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->scene_bytes = (uint32_t) (blob.size() * 16);
+    h->mesh_valid = false;
+    return configure_kernels(h);
+}
+
+int sdm_create(int device_ordinal, SdmHandle** out_handle) {
+    if (!out_handle) return fail(SDM_ERR_INVALID, "null out_handle");
+    *out_handle = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SDM_ERR_NO_DEVICE, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device_ordinal < 0 || device_ordinal >= ndev) return fail(SDM_ERR_INVALID, "device ordinal out of range");
+    CK(cudaSetDevice(device_ordinal));
+    SdmHandle* h = new SdmHandle();
+    h->device = device_ordinal;
+    int rc = SDM_OK;
+    do {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaGetDeviceProperties"); break; }
+        h->num_sms = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "stream"); break; }
+        cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+        if (cudaMallocHost(&h->host_state, sizeof(DevState)) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMallocHost"); break; }
+        memset(h->host_state, 0, sizeof(DevState));
+        if (h->state.reserve(1) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc state"); break; }
+        cudaMemsetAsync(h->state.p, 0, sizeof(DevState), h->stream);
+        cudaMemcpyToSymbolAsync(c_mc_packed, SDM_MC_PACKED_INIT, sizeof(SDM_MC_PACKED_INIT), 0, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyToSymbolAsync(c_mc_edgemask, SDM_MC_EDGEMASK_INIT, sizeof(SDM_MC_EDGEMASK_INIT), 0, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyToSymbolAsync(c_mc_ntri, SDM_MC_NTRI_INIT, sizeof(SDM_MC_NTRI_INIT), 0, cudaMemcpyHostToDevice, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, std::string("init: ") + cudaGetErrorString(cudaGetLastError())); break; }
+        SdmPrimitive def[2];
+        sdm_scene_default(def, 2);
+        rc = sdm_set_scene(h, def, 2);
+        if (rc) break;
+        rc = ensure_capacity(h, 1u << 21);
+    } while (0);
+    if (rc) { sdm_destroy(h); return rc; }
+    *out_handle = h;
+    return SDM_OK;
+}
+
+void sdm_destroy(SdmHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->scene.release(); h->vox[0].release(); h->vox[1].release(); h->cases.release(); h->tri_off.release(); h->slot_ref.release();
+    h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
+    h->tri_valid_bits.release(); h->tri_prefix.release(); h->out_idx.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
+    h->out_pos.release(); h->out_nrm.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->state.release();
+    if (h->host_state) cudaFreeHost(h->host_state);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ---- probes ------------------------------------------------------------------------------------------
+static int eval_common(SdmHandle* h, const float* points, uint32_t n, float* out, int width, int which, uint32_t* iters) {
+    if (!h || !points || !out) return fail(SDM_ERR_INVALID, "null argument");
+    if (n == 0) return SDM_OK;
+    CK(cudaSetDevice(h->device));
+    float *d_in = nullptr, *d_out = nullptr;
+    uint32_t* d_it = nullptr;
+    CK(cudaMalloc(&d_in, (size_t) n * 12));
+    CK(cudaMalloc(&d_out, (size_t) n * 4 * width));
+    if (iters) CK(cudaMalloc(&d_it, (size_t) n * 4));
+    CK(cudaMemcpyAsync(d_in, points, (size_t) n * 12, cudaMemcpyHostToDevice, h->stream));
+    const int grid = std::min<uint32_t>((n + 127) / 128, (uint32_t) h->num_sms * 8);
+    if (which == 0) k_eval_sdf<<<grid, 128, smem_for(h), h->stream>>>(h->scene.p, d_in, n, d_out);
+    else if (which == 1) k_eval_normal<<<grid, 128, smem_for(h), h->stream>>>(h->scene.p, d_in, n, d_out);
+    else k_eval_project<<<grid, 128, smem_for(h), h->stream>>>(h->scene.p, d_in, n, d_out, d_it);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, (size_t) n * 4 * width, cudaMemcpyDeviceToHost, h->stream));
+    if (iters) CK(cudaMemcpyAsync(iters, d_it, (size_t) n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_in); cudaFree(d_out); if (d_it) cudaFree(d_it);
+    return SDM_OK;
+}
+int sdm_eval_sdf(SdmHandle* h, const float* points, uint32_t n, float* out_sd) { return eval_common(h, points, n, out_sd, 1, 0, nullptr); }
+int sdm_eval_normal(SdmHandle* h, const float* points, uint32_t n, float* out_normals) { return eval_common(h, points, n, out_normals, 3, 1, nullptr); }
+int sdm_eval_project(SdmHandle* h, const float* points, uint32_t n, float* out_points, uint32_t* out_iters) {
+    return eval_common(h, points, n, out_points, 3, 2, out_iters);
+}
+
+// ---- host-buffer surface (CudaHandler semantics) --------------------------------------------------------
+int sdm_create_voxel_field(const SdmParams* params, SdmVoxelField* out_field) {
+    if (!out_field) return fail(SDM_ERR_INVALID, "null out_field");
+    SdmParams p { SDM_MESH_GENERATION_BB_SIZE, SDM_MESH_GENERATION_INIT_FACTOR, 0 };
+    if (params) p = *params;
+    int rc = check_params(p);
+    if (rc) return rc;
+    const uint32_t N = p.init_factor;
+    const float size = p.bb_size / (float) N;   // src/cuda/mod.rs:106
+    const size_t n = (size_t) N * N * N;
+    SdmPoint* v = (SdmPoint*) malloc(std::max<size_t>(n, 1) * sizeof(SdmPoint));
+    if (!v) return fail(SDM_ERR_INVALID, "out of host memory");
+    size_t o = 0;
+    for (uint32_t x = 0; x < N; x++)          // x outer, z inner (:110-119)
+        for (uint32_t y = 0; y < N; y++)
+            for (uint32_t z = 0; z < N; z++, o++) {
+                v[o].x = (float) x * size - p.bb_size / 2.0f;
+                v[o].y = (float) y * size - p.bb_size / 2.0f;
+                v[o].z = (float) z * size - p.bb_size / 2.0f;
+            }
+    out_field->voxel_size = SdmPoint { size, size, size };
+    out_field->voxels = v;
+    out_field->voxel_count = (unsigned int) n;
+    return SDM_OK;
+}
+void sdm_voxel_field_free(SdmVoxelField* field) {
+    if (field && field->voxels) { free(field->voxels); field->voxels = nullptr; field->voxel_count = 0; }
+}
+
+int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field) {
+    if (!h || !field || (!field->voxels && field->voxel_count)) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    uint32_t want = h->cap_vox;
+    while (want < field->voxel_count) want = grown(want);
+    int rc = ensure_capacity(h, want);
+    if (rc) return rc;
+    rc = reset_state(h);
+    if (rc) return rc;
+    if (field->voxel_count)
+        CK(cudaMemcpyAsync(h->vox[0].p, field->voxels, (size_t) field->voxel_count * 12, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(&h->state.p->level_count[0], &field->voxel_count, 4, cudaMemcpyHostToDevice, h->stream));
+    h->cur = 0; h->level = 0;
+    h->voxel_size[0] = field->voxel_size.x; h->voxel_size[1] = field->voxel_size.y; h->voxel_size[2] = field->voxel_size.z;
+    h->have_field = true; h->mesh_valid = false;
+    CK(cudaStreamSynchronize(h->stream));   // the host list may be freed by the caller right after
+    return SDM_OK;
+}
+
+int sdm_field_reset(SdmHandle* h, const SdmParams* params) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    SdmParams p { SDM_MESH_GENERATION_BB_SIZE, SDM_MESH_GENERATION_INIT_FACTOR, 0 };
+    if (params) p = *params;
+    int rc = check_params(p);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    uint32_t want = h->cap_vox;
+    const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
+    while (want < n0) want = grown(want);
+    rc = ensure_capacity(h, want);
+    if (rc) return rc;
+    rc = reset_state(h);
+    if (rc) return rc;
+    return enqueue_init_field(h, p);
+}
+
+int sdm_field_refine(SdmHandle* h, uint32_t* out_count) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    if (!h->have_field) return fail(SDM_ERR_STATE, "no device field: call sdm_field_reset / sdm_field_upload first");
+    CK(cudaSetDevice(h->device));
+    // a level can at most multiply the list by 8; grow-and-retry keeps the reference's "always fits" behaviour
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int rc = enqueue_refine(h);
+        if (rc) return rc;
+        uint32_t flags = 0;
+        rc = fetch_state(h, &flags);
+        if (rc) return rc;
+        if (!(flags & ERR_VOXEL_CAP)) {
+            if (out_count) *out_count = h->host_state->level_count[h->level];
+            fill_stats(h, false);
+            return SDM_OK;
+        }
+        // overflow: download the parent list, grow, re-upload, retry
+        const int parent_level = h->level - 1;
+        const uint32_t n_parent = h->host_state->level_count[parent_level];
+        std::vector<float> parents((size_t) n_parent * 3);
+        CK(cudaMemcpy(parents.data(), h->vox[h->cur ^ 1].p, parents.size() * 4, cudaMemcpyDeviceToHost));
+        const float ps[3] = { h->voxel_size[0] * 2.0f, h->voxel_size[1] * 2.0f, h->voxel_size[2] * 2.0f };
+        SdmVoxelField f { SdmPoint { ps[0], ps[1], ps[2] }, (SdmPoint*) parents.data(), n_parent };
+        rc = ensure_capacity(h, grown(h->cap_vox));
+        if (rc) return rc;
+        rc = sdm_field_upload(h, &f);
+        if (rc) return rc;
+    }
+    return fail(SDM_ERR_CAPACITY, "voxel list does not fit in device memory");
+}
+
+int sdm_field_count(SdmHandle* h, uint32_t* out_count, SdmPoint* out_voxel_size) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    if (!h->have_field) return fail(SDM_ERR_STATE, "no device field");
+    CK(cudaSetDevice(h->device));
+    uint32_t flags = 0;
+    int rc = fetch_state(h, &flags);
+    if (rc) return rc;
+    if (out_count) *out_count = h->host_state->level_count[h->level];
+    if (out_voxel_size) *out_voxel_size = SdmPoint { h->voxel_size[0], h->voxel_size[1], h->voxel_size[2] };
+    return SDM_OK;
+}
+
+int sdm_field_download(SdmHandle* h, SdmPoint* out_voxels, uint32_t capacity) {
+    uint32_t n = 0;
+    int rc = sdm_field_count(h, &n, nullptr);
+    if (rc) return rc;
+    if (n > capacity) return fail(SDM_ERR_INVALID, "capacity too small");
+    if (n) CK(cudaMemcpy(out_voxels, h->vox[h->cur].p, (size_t) n * 12, cudaMemcpyDeviceToHost));
+    return SDM_OK;
+}
+
+static int run_mesh(SdmHandle* h, SdmMesh* out_mesh, bool timed) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        if (timed) CK(cudaEventRecord(h->ev0, h->stream));
+        int rc = enqueue_mesh(h);
+        if (rc) return rc;
+        if (timed) CK(cudaEventRecord(h->ev1, h->stream));
+        uint32_t flags = 0;
+        rc = fetch_state(h, &flags);
+        if (rc) return rc;
+        if (!flags) {
+            if (timed) { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.last_gpu_ms = ms; }
+            h->mesh_valid = true;
+            fill_stats(h, true);
+            if (out_mesh) mesh_view(h, out_mesh);
+            return SDM_OK;
+        }
+        // a mesh-stage capacity was exceeded: keep the field (download / grow / upload) and retry
+        const uint32_t n = h->host_state->level_count[h->level];
+        std::vector<float> list((size_t) n * 3);
+        if (n) CK(cudaMemcpy(list.data(), h->vox[h->cur].p, list.size() * 4, cudaMemcpyDeviceToHost));
+        SdmVoxelField f { SdmPoint { h->voxel_size[0], h->voxel_size[1], h->voxel_size[2] }, (SdmPoint*) list.data(), n };
+        rc = ensure_capacity(h, grown(h->cap_vox));
+        if (rc) return rc;
+        rc = sdm_field_upload(h, &f);
+        if (rc) return rc;
+    }
+    return fail(SDM_ERR_CAPACITY, "mesh does not fit in device memory");
+}
+
+int sdm_field_to_mesh(SdmHandle* h, SdmMesh* out_mesh) {
+    if (!h || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
+    if (!h->have_field) return fail(SDM_ERR_STATE, "no device field");
+    CK(cudaSetDevice(h->device));
+    return run_mesh(h, out_mesh, true);
+}
+
+int sdm_field_cases(SdmHandle* h, uint8_t* out_cases, uint32_t capacity) {
+    if (!h || !out_cases) return fail(SDM_ERR_INVALID, "null argument");
+    if (!h->mesh_valid) return fail(SDM_ERR_STATE, "no mesh: call sdm_field_to_mesh / sdm_remesh first");
+    const uint32_t n = h->host_state->level_count[h->level];
+    if (n > capacity) return fail(SDM_ERR_INVALID, "capacity too small");
+    CK(cudaSetDevice(h->device));
+    if (n) CK(cudaMemcpy(out_cases, h->cases.p, n, cudaMemcpyDeviceToHost));
+    return SDM_OK;
+}
+
+int sdm_field_triangle_soup(SdmHandle* h, SdmTriangle* out_triangles, uint32_t capacity) {
+    if (!h || !out_triangles) return fail(SDM_ERR_INVALID, "null argument");
+    if (!h->mesh_valid) return fail(SDM_ERR_STATE, "no mesh: call sdm_field_to_mesh / sdm_remesh first");
+    const uint32_t n = h->host_state->level_count[h->level];
+    if ((uint64_t) n * 5 > capacity) return fail(SDM_ERR_INVALID, "capacity too small");
+    if (n == 0) return SDM_OK;
+    CK(cudaSetDevice(h->device));
+    float* d = nullptr;
+    CK(cudaMalloc(&d, (size_t) n * 5 * sizeof(SdmTriangle)));
+    k_soup<<<h->g_light, 256, 0, h->stream>>>(h->state.p, h->level, h->cases.p, h->tri_off.p, h->tri_uid.p, h->upos.p, h->unrm.p, d);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_triangles, d, (size_t) n * 5 * sizeof(SdmTriangle), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    return SDM_OK;
+}
+
+int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
+    if (!h || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
+    SdmParams p { SDM_MESH_GENERATION_BB_SIZE, SDM_MESH_GENERATION_INIT_FACTOR, 0 };
+    if (params) p = *params;
+    int rc = check_params(p);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    uint32_t want = h->cap_vox;
+    const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
+    while (want < n0) want = grown(want);
+    for (int attempt = 0; attempt < 10; attempt++) {
+        rc = ensure_capacity(h, want);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev0, h->stream));
+        rc = reset_state(h);
+        if (rc) return rc;
+        rc = enqueue_init_field(h, p);
+        if (rc) return rc;
+        for (uint32_t l = 0; l < p.levels; l++) {
+            rc = enqueue_refine(h);
+            if (rc) return rc;
+        }
+        rc = enqueue_mesh(h);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev1, h->stream));
+        uint32_t flags = 0;
+        rc = fetch_state(h, &flags);
+        if (rc) return rc;
+        if (!flags) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            h->stats.last_gpu_ms = ms;
+            h->mesh_valid = true;
+            fill_stats(h, true);
+            mesh_view(h, out_mesh);
+            return SDM_OK;
+        }
+        want = grown(h->cap_vox);
+        if (want == h->cap_vox) break;
+    }
+    return fail(SDM_ERR_CAPACITY, "remesh does not fit in device memory");
+}
+
+int sdm_mesh_download(SdmHandle* h, const SdmMesh* m, float* positions, float* normals, uint32_t* indices) {
+    if (!h || !m) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    if (m->vertex_count && positions) CK(cudaMemcpyAsync(positions, m->positions, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, h->stream));
+    if (m->vertex_count && normals) CK(cudaMemcpyAsync(normals, m->normals, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, h->stream));
+    if (m->triangle_count && indices) CK(cudaMemcpyAsync(indices, m->indices, (size_t) m->triangle_count * 12, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SDM_OK;
+}
+
+int sdm_refine_voxel_field(SdmHandle* h, SdmVoxelField* field) {
+    if (!h || !field) return fail(SDM_ERR_INVALID, "null argument");
+    if (field->voxel_count == 0) return SDM_OK;   // src/cuda/mod.rs:137: size is NOT halved for an empty field
+    int rc = sdm_field_upload(h, field);
+    if (rc) return rc;
+    uint32_t n = 0;
+    rc = sdm_field_refine(h, &n);
+    if (rc) return rc;
+    SdmPoint* v = (SdmPoint*) malloc(std::max<size_t>(n, 1) * sizeof(SdmPoint));
+    if (!v) return fail(SDM_ERR_INVALID, "out of host memory");
+    rc = sdm_field_download(h, v, n);
+    if (rc) { free(v); return rc; }
+    free(field->voxels);
+    field->voxels = v;
+    field->voxel_count = n;
+    field->voxel_size = SdmPoint { h->voxel_size[0], h->voxel_size[1], h->voxel_size[2] };
+    return SDM_OK;
+}
+
+int sdm_voxel_field_to_mesh(SdmHandle* h, const SdmVoxelField* field, SdmMesh* out_mesh) {
+    if (!h || !field || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
+    memset(out_mesh, 0, sizeof(*out_mesh));
+    if (field->voxel_count == 0) return SDM_OK;   // empty mesh (src/cuda/mod.rs:327-345)
+    int rc = sdm_field_upload(h, field);
+    if (rc) return rc;
+    SdmMesh dm;
+    rc = run_mesh(h, &dm, true);
+    if (rc) return rc;
+    out_mesh->vertex_count = dm.vertex_count;
+    out_mesh->triangle_count = dm.triangle_count;
+    out_mesh->positions = (float*) malloc(std::max<size_t>(dm.vertex_count, 1) * 12);
+    out_mesh->normals = (float*) malloc(std::max<size_t>(dm.vertex_count, 1) * 12);
+    out_mesh->indices = (uint32_t*) malloc(std::max<size_t>(dm.triangle_count, 1) * 12);
+    if (!out_mesh->positions || !out_mesh->normals || !out_mesh->indices) { sdm_mesh_free(out_mesh); return fail(SDM_ERR_INVALID, "out of host memory"); }
+    return sdm_mesh_download(h, &dm, out_mesh->positions, out_mesh->normals, out_mesh->indices);
+}
+
+void sdm_mesh_free(SdmMesh* mesh) {
+    if (!mesh || mesh->on_device) return;
+    free(mesh->positions); free(mesh->normals); free(mesh->indices);
+    memset(mesh, 0, sizeof(*mesh));
+}
+
+int sdm_field_take_shard(SdmHandle* h, uint32_t shard_index, uint32_t shard_count) {
+    (void) h; (void) shard_index; (void) shard_count;
+    return fail(SDM_ERR_STATE, "sdm_field_take_shard: not implemented yet");
+}
+
+int sdm_get_stats(SdmHandle* h, SdmStats* out) {
+    if (!h || !out) return fail(SDM_ERR_INVALID, "null argument");
+    *out = h->stats;
+    return SDM_OK;
+}
+
+}  // extern "C"

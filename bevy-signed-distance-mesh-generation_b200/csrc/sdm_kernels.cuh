@@ -1,0 +1,579 @@
+// sdm_kernels.cuh - the sm_100a kernels of the mesh-generation path.
+//
+//   k_init_field      level-0 dense list                       (src/cuda/mod.rs:105-122)
+//   k_refine          3x3x3 lattice classification + stable compaction of surviving children
+//                     (compute_mesh_generation.cu:12-62 + src/cuda/mod.rs:179-194)
+//   k_classify        8 corner signs -> case index, triangle count, triangle offsets
+//                     (compute_mesh_generation.cu:77-86, marching_cubes.cu:19-25)
+//   k_edges           edge mid-points (marching_cubes.cu:13-16) de-duplicated by exact bit pattern
+//   k_project         closest_surface_point per distinct mid-point (signed_distance.cu:227-240)
+//   k_vertex_normals  empirical_normal per projected vertex (signed_distance.cu:181-202)
+//   k_orient          per triangle: face normal vs. centroid normal, flip (compute_mesh_generation.cu:103-113),
+//                     finite filter (src/cuda/mod.rs:289), first-occurrence slot per vertex
+//   k_weld_insert / k_weld_mark / k_bitscan / k_emit_*   the reference-order weld (src/cuda/mod.rs:263-296)
+//   k_soup            the reference's raw 5-slot Triangle format (compute_mesh_generation.cu:107-118)
+//
+// All kernels are persistent (grid = SMs x resident blocks) and read their problem sizes from DevState in
+// device memory, so that a whole remesh is enqueued without any host synchronisation.
+#pragma once
+
+#include "sdm_device.cuh"
+#include "mc_tables.inc"
+
+namespace sdm {
+
+enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_COUNT = 24 };
+enum ErrFlag : uint32_t {
+    ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u
+};
+
+struct DevState {
+    uint32_t level_count[17];   // active voxels per level (index = level)
+    uint32_t n_tris_raw;        // triangles before the finite filter
+    uint32_t n_uniq;            // distinct edge mid-points
+    uint32_t n_tris_out;        // triangles after the finite filter
+    uint32_t n_verts_out;       // welded vertices
+    uint32_t error_flags;
+    uint32_t ticket[TK_COUNT];
+    uint32_t pad;
+    unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
+};
+
+// Marching-cubes tables staged per block
+struct McShared {
+    unsigned long long packed[256];
+    unsigned short edgemask[256];
+    unsigned char ntri[256];
+};
+__constant__ unsigned long long c_mc_packed[256];
+__constant__ unsigned short c_mc_edgemask[256];
+__constant__ unsigned char c_mc_ntri[256];
+
+__device__ __forceinline__ void stage_mc(McShared* s) {
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        s->packed[i] = c_mc_packed[i];
+        s->edgemask[i] = c_mc_edgemask[i];
+        s->ntri[i] = c_mc_ntri[i];
+    }
+    __syncthreads();
+}
+
+// corner c of a voxel (compute_mesh_generation.cu:77-86): +x iff c%4 in {1,2}, +y iff c%4 >= 2, +z iff c >= 4.
+// The zero is added too (v[0] += cond ? size : 0.0f), exactly as in the reference.
+__device__ __forceinline__ void voxel_corner(float bx, float by, float bz, float sx, float sy, float sz, int c, float& x, float& y, float& z) {
+    const int c4 = c & 3;
+    x = bx + ((c4 == 1 || c4 == 2) ? sx : 0.0f);
+    y = by + ((c4 >= 2) ? sy : 0.0f);
+    z = bz + ((c >= 4) ? sz : 0.0f);
+}
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_init_field(float* __restrict__ vox, DevState* st, float bb_size, uint32_t init, float size,
+                                                    uint32_t cap_vox) {
+    const uint64_t n = (uint64_t) init * init * init;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->level_count[0] = (uint32_t) (n <= cap_vox ? n : 0);
+        if (n > cap_vox) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
+    }
+    if (n > cap_vox) return;
+    const float half = bb_size / 2.0f;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t z = (uint32_t) (i % init), y = (uint32_t) ((i / init) % init), x = (uint32_t) (i / ((uint64_t) init * init));
+        vox[3 * i + 0] = (float) x * size - half;   // src/cuda/mod.rs:114-116
+        vox[3 * i + 1] = (float) y * size - half;
+        vox[3 * i + 2] = (float) z * size - half;
+    }
+}
+
+// Corner masks of the 8 children inside the parent's 3x3x3 lattice; lattice index l = a*9 + b*3 + c (a: x, b: y, c: z).
+__device__ __forceinline__ constexpr uint32_t child_mask(int i, int j, int k) {
+    uint32_t m = 0;
+    for (int di = 0; di < 2; di++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int dk = 0; dk < 2; dk++) m |= 1u << ((i + di) * 9 + (j + dj) * 3 + (k + dk));
+    return m;
+}
+
+// One warp = one tile of 32 parents.  864 lattice points are spread over the 32 lanes (27 rounds), each round's
+// inside-bits are gathered with one ballot; lane q then owns parent q's 27-bit mask.
+__global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox,
+                                                float* __restrict__ out_vox, DevState* st, int level, uint32_t epoch,
+                                                uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = st->level_count[level];
+    const uint32_t ntiles = (n + 31u) >> 5;
+    while (true) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&st->ticket[TK_REFINE0 + level], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) {
+            if (tile == 0 && lane == 0) st->level_count[level + 1] = 0;   // empty input: no-op (src/cuda/mod.rs:137)
+            break;
+        }
+        const uint32_t p0 = tile << 5;
+        const uint32_t np = min(32u, n - p0);
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        if (lane < np) {
+            bx = in_vox[3 * (size_t) (p0 + lane) + 0];
+            by = in_vox[3 * (size_t) (p0 + lane) + 1];
+            bz = in_vox[3 * (size_t) (p0 + lane) + 2];
+        }
+        uint32_t myword = 0;
+        const uint32_t rounds = (27u * np + 31u) >> 5;
+        for (uint32_t t = 0; t < rounds; t++) {
+            const uint32_t idx = (t << 5) + lane;
+            const uint32_t q = idx / 27u;
+            const uint32_t l = idx - q * 27u;
+            const float qx = __shfl_sync(0xffffffffu, bx, q & 31u);
+            const float qy = __shfl_sync(0xffffffffu, by, q & 31u);
+            const float qz = __shfl_sync(0xffffffffu, bz, q & 31u);
+            const uint32_t a = l / 9u, b = (l / 3u) % 3u, c = l % 3u;
+            // base + vec3{i,j,k} * output_voxel_size (compute_mesh_generation.cu:33-34); lattice step 2 is the
+            // `upper` of child 1 (i+1 = 2), step 1 is both `upper` of child 0 and `lower` of child 1.
+            const float x = qx + (float) a * osx, y = qy + (float) b * osy, z = qz + (float) c * osz;
+            bool inside = false;
+            if (q < np) inside = eval_scene1(sc, x, y, z) <= 0.0f;   // obj_contains, :8-10
+            const uint32_t w = __ballot_sync(0xffffffffu, inside);
+            if (lane == t) myword = w;
+        }
+        const uint32_t bit0 = lane * 27u;
+        const uint32_t w0 = bit0 >> 5, sh = bit0 & 31u;
+        const uint32_t lo = __shfl_sync(0xffffffffu, myword, w0);
+        const uint32_t hi = __shfl_sync(0xffffffffu, myword, (w0 + 1u) & 31u);
+        const uint32_t m27 = (uint32_t) ((((uint64_t) hi << 32) | lo) >> sh) & 0x7FFFFFFu;
+        uint32_t keep = 0;
+        if (lane < np) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) {
+                const uint32_t M = child_mask(ch >> 2, (ch >> 1) & 1, ch & 1);
+                const uint32_t s = m27 & M;
+                keep |= (uint32_t) (s != 0u && s != M) << ch;   // is_border: corners do not all agree (:36-49)
+            }
+        }
+        const uint32_t cnt = __popc(keep);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t) o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
+        uint32_t pos = excl_tile + incl - cnt;
+        if (excl_tile + total > cap_vox) {
+            if (lane == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) {   // child order n_id = id*8 + i*4 + j*2 + k (:51); stable
+                if (keep & (1u << ch)) {
+                    out_vox[3 * (size_t) pos + 0] = bx + (float) (ch >> 2) * osx;
+                    out_vox[3 * (size_t) pos + 1] = by + (float) ((ch >> 1) & 1) * osy;
+                    out_vox[3 * (size_t) pos + 2] = bz + (float) (ch & 1) * osz;
+                    pos++;
+                }
+            }
+        }
+        if (tile == ntiles - 1 && lane == 0) st->level_count[level + 1] = min(excl_tile + total, cap_vox);
+    }
+}
+
+// One warp = 32 voxels = 256 corner samples = 8 ballots; voxel q's case byte is byte (q&3) of ballot (q>>2).
+__global__ void __launch_bounds__(256) k_classify(const uint4* __restrict__ scene, const float* __restrict__ vox, DevState* st,
+                                                  int level, uint32_t epoch, uint64_t* tiles, uint8_t* __restrict__ cases,
+                                                  uint32_t* __restrict__ tri_off, uint32_t cap_tris, float sx, float sy, float sz) {
+    extern __shared__ uint4 smem[];
+    __shared__ unsigned char s_ntri[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = c_mc_ntri[i];
+    const SceneView sc = stage_scene(scene, smem);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = st->level_count[level];
+    const uint32_t ntiles = (n + 31u) >> 5;
+    while (true) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) {
+            if (tile == 0 && lane == 0) st->n_tris_raw = 0;
+            break;
+        }
+        const uint32_t p0 = tile << 5;
+        const uint32_t np = min(32u, n - p0);
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        if (lane < np) {
+            bx = vox[3 * (size_t) (p0 + lane) + 0];
+            by = vox[3 * (size_t) (p0 + lane) + 1];
+            bz = vox[3 * (size_t) (p0 + lane) + 2];
+        }
+        uint32_t myword = 0;
+#pragma unroll 1
+        for (uint32_t t = 0; t < 8; t++) {
+            const uint32_t idx = (t << 5) + lane;
+            const uint32_t q = idx >> 3;
+            const int c = (int) (idx & 7u);
+            const float qx = __shfl_sync(0xffffffffu, bx, q);
+            const float qy = __shfl_sync(0xffffffffu, by, q);
+            const float qz = __shfl_sync(0xffffffffu, bz, q);
+            float x, y, z;
+            voxel_corner(qx, qy, qz, sx, sy, sz, c, x, y, z);
+            bool inside = false;
+            if (q < np) inside = eval_scene1(sc, x, y, z) <= 0.0f;   // marching_cubes.cu:22
+            const uint32_t w = __ballot_sync(0xffffffffu, inside);
+            if (lane == t) myword = w;
+        }
+        const uint32_t w = __shfl_sync(0xffffffffu, myword, lane >> 2);
+        const uint32_t cube_index = (w >> ((lane & 3u) * 8u)) & 0xFFu;
+        const uint32_t cnt = lane < np ? s_ntri[cube_index] : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t) o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
+        if (lane < np) {
+            cases[p0 + lane] = (uint8_t) cube_index;
+            tri_off[p0 + lane] = excl_tile + incl - cnt;
+        }
+        if (tile == ntiles - 1 && lane == 0) {
+            const uint32_t T = excl_tile + total;
+            if (T > cap_tris) atomicOr(&st->error_flags, ERR_TRI_CAP);
+            st->n_tris_raw = min(T, cap_tris);
+        }
+    }
+}
+
+// Edge mid-points, de-duplicated by the exact bit pattern of the mid-point (identical start point => identical
+// projection, normal and weld key; mid-points that differ in any bit stay separate and are merged, if at all,
+// by the quantised weld exactly as in the reference).
+__global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
+                                               const uint32_t* __restrict__ tri_off, uint4* table, uint32_t table_mask,
+                                               float* __restrict__ ustart, uint32_t cap_uniq, uint32_t* __restrict__ slot_ref,
+                                               float sx, float sy, float sz) {
+    __shared__ McShared mc;
+    stage_mc(&mc);
+    const uint32_t n = st->level_count[level];
+    if (st->error_flags & ERR_TRI_CAP) return;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const uint32_t cube_index = cases[v];
+        const uint32_t ntri = mc.ntri[cube_index];
+        if (ntri == 0) continue;
+        const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
+        const uint32_t emask = mc.edgemask[cube_index];
+        uint32_t eref[12];
+#pragma unroll
+        for (int e = 0; e < 12; e++) {
+            eref[e] = 0xFFFFFFFFu;
+            if (emask & (1u << e)) {
+                // MC_EDGE_TABLE (marching_cubes_constants.cu:3-16)
+                const int c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
+                const int c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
+                float ax, ay, az, cx, cy, cz;
+                voxel_corner(bx, by, bz, sx, sy, sz, c0, ax, ay, az);
+                voxel_corner(bx, by, bz, sx, sy, sz, c1, cx, cy, cz);
+                // mix(a, b, 0.5f) = a * (1.0f - 0.5f) + b * 0.5f   (marching_cubes.cu:13-16)
+                const float mx = ax * (1.0f - 0.5f) + cx * 0.5f, my = ay * (1.0f - 0.5f) + cy * 0.5f, mz = az * (1.0f - 0.5f) + cz * 0.5f;
+                uint32_t kx = __float_as_uint(mx), ky = __float_as_uint(my), kz = __float_as_uint(mz);
+                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
+                bool won;
+                const uint32_t pos = hash_find_or_insert(table, table_mask, kx, ky, kz, 0xFFFFFFFEu, &won);
+                if (pos == 0xFFFFFFFFu) { atomicOr(&st->error_flags, ERR_HASH_FULL); continue; }
+                if (won) {
+                    const uint32_t uid = atomicAdd(&st->n_uniq, 1u);
+                    if (uid < cap_uniq) {
+                        ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
+                    } else {
+                        atomicOr(&st->error_flags, ERR_UNIQ_CAP);
+                    }
+                    reinterpret_cast<uint32_t*>(table + pos)[3] = uid;   // readers come after the kernel boundary
+                }
+                eref[e] = pos;
+            }
+        }
+        const unsigned long long packed = mc.packed[cube_index];
+        const uint32_t t0 = tri_off[v];
+        for (uint32_t j = 0; j < 3 * ntri; j++) {
+            const int e = (int) ((packed >> (4 * j)) & 0xFull);
+            uint32_t r = 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < 12; q++) if (q == e) r = eref[q];
+            slot_ref[3 * (size_t) t0 + j] = r;
+        }
+    }
+}
+
+// closest_surface_point per distinct mid-point.  Lanes that finish pull the next vertex (warp-level refill from a
+// global ticket), so a warp's lanes stay busy although iteration counts differ per vertex.
+__global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart,
+                                                 float* __restrict__ upos, uint32_t cap_uniq) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    bool have = false;
+    uint32_t uid = 0, it = 0, iters_done = 0;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    bool drained = false;
+    while (true) {
+        const uint32_t need = __ballot_sync(0xffffffffu, !have);
+        if (need && !drained) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&st->ticket[TK_PROJECT], (uint32_t) __popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!have) {
+                const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
+                if (idx < n) {
+                    uid = idx; it = 0; have = true;
+                    gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
+                }
+            }
+            if (base + __popc(need) >= n) drained = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            const bool collision = newton_step(sc, gx, gy, gz);
+            it++;
+            if (collision || it >= 10000u) {   // for (i = 0; !collision && i < 10000; i++)
+                upos[3 * (size_t) uid] = gx; upos[3 * (size_t) uid + 1] = gy; upos[3 * (size_t) uid + 2] = gz;
+                iters_done += it;
+                have = false;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) iters_done += __shfl_xor_sync(0xffffffffu, iters_done, o);
+    if (lane == 0 && iters_done) atomicAdd(&st->newton_iters, (unsigned long long) iters_done);
+}
+
+__global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
+                                                        float* __restrict__ unrm, uint32_t cap_uniq) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        float nx, ny, nz;
+        empirical_normal(sc, upos[3 * (size_t) u], upos[3 * (size_t) u + 1], upos[3 * (size_t) u + 2], nx, ny, nz);
+        unrm[3 * (size_t) u] = nx; unrm[3 * (size_t) u + 1] = ny; unrm[3 * (size_t) u + 2] = nz;
+    }
+}
+
+// Per raw triangle: orientation test and the reference host's triangle filter.
+__global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene, DevState* st, const uint4* __restrict__ table,
+                                                const uint32_t* __restrict__ slot_ref, const float* __restrict__ upos,
+                                                uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
+                                                uint32_t* __restrict__ tri_valid_bits) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    const uint32_t T = st->n_tris_raw;
+    if (st->error_flags) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    // warp-contiguous mapping so that one lane can write the 32 validity bits of a warp's triangles
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t t0 = warp_id << 5; t0 < T; t0 += warps_total << 5) {
+        const uint32_t t = t0 + lane;
+        bool valid = false;
+        if (t < T) {
+            uint32_t u[3];
+            float v[3][3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                u[j] = reinterpret_cast<const uint32_t*>(table + slot_ref[3 * (size_t) t + j])[3];
+                v[j][0] = upos[3 * (size_t) u[j]]; v[j][1] = upos[3 * (size_t) u[j] + 1]; v[j][2] = upos[3 * (size_t) u[j] + 2];
+            }
+            // normalize(cross(v1 - v0, v2 - v0))   (compute_mesh_generation.cu:103)
+            const float ax = v[1][0] - v[0][0], ay = v[1][1] - v[0][1], az = v[1][2] - v[0][2];
+            const float bx = v[2][0] - v[0][0], by = v[2][1] - v[0][1], bz = v[2][2] - v[0][2];
+            const float cx = ay * bz - by * az, cy = az * bx - bz * ax, cz = ax * by - bx * ay;
+            const float inv = 1.0f / sqrtf(dot3(cx, cy, cz, cx, cy, cz));
+            const float tnx = cx * inv, tny = cy * inv, tnz = cz * inv;
+            // empirical_normal(sd_obj, (v0 + v1 + v2) / 3.0f)   (:104)
+            const float mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f, my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f,
+                        mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
+            float nx, ny, nz;
+            empirical_normal(sc, mx, my, mz, nx, ny, nz);
+            const bool flip = dot3(tnx, tny, tnz, nx, ny, nz) <= 0.0f;   // :105
+            const uint32_t f0 = flip ? u[2] : u[0], f2 = flip ? u[0] : u[2];
+            const float first_x = flip ? v[2][0] : v[0][0];
+            tri_uid[3 * (size_t) t] = f0; tri_uid[3 * (size_t) t + 1] = u[1]; tri_uid[3 * (size_t) t + 2] = f2;
+            // src/cuda/mod.rs:289: triangle kept iff vertices[0].position.x is finite
+            valid = fabsf(first_x) <= FLT_MAX;
+            if (valid) {
+                atomicMin(first_slot + f0, 3u * t);
+                atomicMin(first_slot + u[1], 3u * t + 1u);
+                atomicMin(first_slot + f2, 3u * t + 2u);
+            }
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) tri_valid_bits[t0 >> 5] = bits;
+    }
+}
+
+// Weld, step 1: every vertex that is referenced by a kept triangle enters the key table with the smallest slot
+// id (3*triangle + corner, post-flip order) at which it occurs; the table keeps the minimum per key.
+__global__ void __launch_bounds__(256) k_weld_insert(DevState* st, const float* __restrict__ upos, const uint32_t* __restrict__ first_slot,
+                                                     uint4* table, uint32_t table_mask, uint32_t* __restrict__ wref, uint32_t cap_uniq) {
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags) return;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        const uint32_t fs = first_slot[u];
+        if (fs == 0xFFFFFFFFu) { wref[u] = 0xFFFFFFFFu; continue; }
+        const uint32_t kx = weld_key_component(upos[3 * (size_t) u]);
+        const uint32_t ky = weld_key_component(upos[3 * (size_t) u + 1]);
+        const uint32_t kz = weld_key_component(upos[3 * (size_t) u + 2]);
+        bool won;
+        const uint32_t pos = hash_find_or_insert(table, table_mask, kx, ky, kz, fs, &won);
+        if (pos == 0xFFFFFFFFu) { atomicOr(&st->error_flags, ERR_HASH_FULL); wref[u] = 0xFFFFFFFFu; continue; }
+        if (!won) atomicMin(reinterpret_cast<uint32_t*>(table + pos) + 3, fs);
+        wref[u] = pos;
+    }
+}
+// Weld, step 2: the vertex whose first slot equals its key's minimum is the key's first occurrence in the
+// reference's scan order; mark that slot.
+__global__ void __launch_bounds__(256) k_weld_mark(DevState* st, const uint32_t* __restrict__ first_slot, const uint4* __restrict__ table,
+                                                   const uint32_t* __restrict__ wref, uint32_t* first_bits, uint32_t cap_uniq) {
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags) return;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        const uint32_t r = wref[u];
+        if (r == 0xFFFFFFFFu) continue;
+        const uint32_t fs = first_slot[u];
+        if (reinterpret_cast<const uint32_t*>(table + r)[3] == fs) atomicOr(first_bits + (fs >> 5), 1u << (fs & 31u));
+    }
+}
+
+// Exclusive prefix pop-count over a bit mask: word_prefix[w] = number of set bits in words [0, w).
+// which: 0 -> bits cover 3*n_tris_raw slots, total to n_verts_out; 1 -> bits cover n_tris_raw, total to n_tris_out.
+__global__ void __launch_bounds__(256) k_bitscan(DevState* st, const uint32_t* __restrict__ bits, uint32_t* __restrict__ word_prefix,
+                                                 int which, uint32_t epoch, uint64_t* tiles) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nbits = which == 0 ? 3u * st->n_tris_raw : st->n_tris_raw;
+    const uint32_t nwords = (nbits + 31u) >> 5;
+    const uint32_t ntiles = (nwords + 31u) >> 5;
+    uint32_t* total_out = which == 0 ? &st->n_verts_out : &st->n_tris_out;
+    const int tk = which == 0 ? TK_SCAN_FIRST : TK_SCAN_TRI;
+    const bool bad = st->error_flags != 0;
+    while (true) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&st->ticket[tk], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles || bad) {
+            if ((tile == 0 || bad) && lane == 0) *total_out = 0;
+            break;
+        }
+        const uint32_t w = (tile << 5) + lane;
+        const uint32_t cnt = w < nwords ? (uint32_t) __popc(bits[w]) : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t) o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
+        if (w < nwords) word_prefix[w] = excl_tile + incl - cnt;
+        if (tile == ntiles - 1 && lane == 0) *total_out = excl_tile + total;
+    }
+}
+
+__device__ __forceinline__ uint32_t bit_rank(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ word_prefix, uint32_t i) {
+    return word_prefix[i >> 5] + (uint32_t) __popc(bits[i >> 5] & ((1u << (i & 31u)) - 1u));
+}
+
+__global__ void __launch_bounds__(256) k_emit_vertices(DevState* st, const uint32_t* __restrict__ first_slot, const uint4* __restrict__ table,
+                                                       const uint32_t* __restrict__ wref, const uint32_t* __restrict__ first_bits,
+                                                       const uint32_t* __restrict__ first_prefix, const float* __restrict__ upos,
+                                                       const float* __restrict__ unrm, float* __restrict__ out_pos, float* __restrict__ out_nrm,
+                                                       uint32_t cap_uniq) {
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags) return;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        const uint32_t r = wref[u];
+        if (r == 0xFFFFFFFFu) continue;
+        const uint32_t fs = first_slot[u];
+        if (reinterpret_cast<const uint32_t*>(table + r)[3] != fs) continue;
+        const uint32_t rank = bit_rank(first_bits, first_prefix, fs);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            out_pos[3 * (size_t) rank + c] = upos[3 * (size_t) u + c];   // first occurrence decides position AND normal
+            out_nrm[3 * (size_t) rank + c] = unrm[3 * (size_t) u + c];   // (src/cuda/mod.rs:279-284)
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_emit_indices(DevState* st, const uint32_t* __restrict__ tri_uid, const uint4* __restrict__ table,
+                                                      const uint32_t* __restrict__ wref, const uint32_t* __restrict__ first_bits,
+                                                      const uint32_t* __restrict__ first_prefix, const uint32_t* __restrict__ tri_valid_bits,
+                                                      const uint32_t* __restrict__ tri_prefix, uint32_t* __restrict__ out_idx) {
+    const uint32_t T = st->n_tris_raw;
+    if (st->error_flags) return;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        if (!((tri_valid_bits[t >> 5] >> (t & 31u)) & 1u)) continue;
+        const uint32_t ot = bit_rank(tri_valid_bits, tri_prefix, t);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const uint32_t u = tri_uid[3 * (size_t) t + j];
+            const uint32_t fs = reinterpret_cast<const uint32_t*>(table + wref[u])[3];
+            out_idx[3 * (size_t) ot + j] = bit_rank(first_bits, first_prefix, fs);
+        }
+    }
+}
+
+// The reference's device output format: 5 Triangle slots per voxel (compute_mesh_generation.cu:71-72), post-flip
+// vertices (:111-113); unused slots are `{ POINT_NAN, POINT_NAN }` = vertex 0 NaN, vertices 1..2 zero (:116-118).
+__global__ void __launch_bounds__(256) k_soup(DevState* st, int level, const uint8_t* __restrict__ cases, const uint32_t* __restrict__ tri_off,
+                                              const uint32_t* __restrict__ tri_uid, const float* __restrict__ upos, const float* __restrict__ unrm,
+                                              float* __restrict__ out /* n*5*18 */) {
+    const uint32_t n = st->level_count[level];
+    if (st->error_flags) return;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const uint32_t ntri = c_mc_ntri[cases[v]];
+        const uint32_t t0 = tri_off[v];
+        float* o = out + (size_t) v * 90;
+        for (uint32_t t = 0; t < 5; t++) {
+            if (t < ntri) {
+                for (int j = 0; j < 3; j++) {
+                    const uint32_t u = tri_uid[3 * (size_t) (t0 + t) + j];
+                    for (int c = 0; c < 3; c++) {
+                        o[t * 18 + j * 6 + c] = upos[3 * (size_t) u + c];
+                        o[t * 18 + j * 6 + 3 + c] = unrm[3 * (size_t) u + c];
+                    }
+                }
+            } else {
+                for (int q = 0; q < 18; q++) o[t * 18 + q] = q < 6 ? __int_as_float(0x7fc00000) : 0.0f;
+            }
+        }
+    }
+}
+
+// ---- test / probe kernels -------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_eval_sdf(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = eval_scene1(sc, pts[3 * (size_t) i], pts[3 * (size_t) i + 1], pts[3 * (size_t) i + 2]);
+}
+__global__ void __launch_bounds__(128) k_eval_normal(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float nx, ny, nz;
+        empirical_normal(sc, pts[3 * (size_t) i], pts[3 * (size_t) i + 1], pts[3 * (size_t) i + 2], nx, ny, nz);
+        out[3 * (size_t) i] = nx; out[3 * (size_t) i + 1] = ny; out[3 * (size_t) i + 2] = nz;
+    }
+}
+__global__ void __launch_bounds__(128) k_eval_project(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n,
+                                                      float* __restrict__ out, uint32_t* __restrict__ iters) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float gx = pts[3 * (size_t) i], gy = pts[3 * (size_t) i + 1], gz = pts[3 * (size_t) i + 2];
+        uint32_t it = 0;
+        bool collision = false;
+        while (!collision && it < 10000u) { collision = newton_step(sc, gx, gy, gz); it++; }
+        out[3 * (size_t) i] = gx; out[3 * (size_t) i + 1] = gy; out[3 * (size_t) i + 2] = gz;
+        if (iters) iters[i] = it;
+    }
+}
+
+}  // namespace sdm

@@ -1,0 +1,294 @@
+"""ctypes mirror of the reference's ``CudaHandler`` (src/cuda/mod.rs:25-346) over libsdfmesh.so.
+
+Method names, argument meaning and error behaviour follow the Rust host:
+
+=====================================  =========================================================
+reference (src/cuda/mod.rs)            here
+=====================================  =========================================================
+``CudaHandler::new()`` (:49)           ``CudaHandler(device=0)``
+``create_cuda_voxel_field()`` (:105)   ``CudaHandler.create_cuda_voxel_field()``
+``refine_voxel_field(&mut f)`` (:124)  ``handler.refine_voxel_field(field)`` (in place)
+``voxel_field_to_mesh(&f)`` (:204)     ``handler.voxel_field_to_mesh(field) -> Mesh``
+=====================================  =========================================================
+
+plus the device-resident path (``field_reset`` / ``field_refine`` / ``field_to_mesh`` / ``remesh``) that keeps every
+stage in HBM.  There is no CPU fallback: if the library or a CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+import pathlib
+
+import numpy as np
+
+from .scenes import PRIM_DTYPE
+
+_HERE = pathlib.Path(__file__).resolve().parent
+
+
+class SdfMeshError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"sdfmesh error {code}: {message}")
+        self.code = code
+
+
+class _Point(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_float), ("y", ctypes.c_float), ("z", ctypes.c_float)]
+
+
+class _VoxelField(ctypes.Structure):  # bindings.h:51-55
+    _fields_ = [("voxel_size", _Point), ("voxels", ctypes.c_void_p), ("voxel_count", ctypes.c_uint)]
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [("bb_size", ctypes.c_float), ("init_factor", ctypes.c_uint32), ("levels", ctypes.c_uint32)]
+
+
+class _Mesh(ctypes.Structure):
+    _fields_ = [
+        ("positions", ctypes.c_void_p), ("normals", ctypes.c_void_p), ("indices", ctypes.c_void_p),
+        ("vertex_count", ctypes.c_uint32), ("triangle_count", ctypes.c_uint32),
+        ("on_device", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [
+        ("kernel_launches", ctypes.c_uint64), ("sdf_evals", ctypes.c_uint64), ("level_counts", ctypes.c_uint32 * 16),
+        ("unique_vertices", ctypes.c_uint32), ("raw_triangles", ctypes.c_uint32), ("last_gpu_ms", ctypes.c_float),
+        ("reserved", ctypes.c_uint32),
+    ]
+
+
+assert ctypes.sizeof(_VoxelField) == 32 and _VoxelField.voxels.offset == 16 and _VoxelField.voxel_count.offset == 24
+
+# every symbol include/sdfmesh.h declares (tests/test_abi.py checks the library exports each one)
+ABI_SYMBOLS = [
+    "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_scene_default", "sdm_set_scene", "sdm_eval_sdf",
+    "sdm_eval_normal", "sdm_eval_project", "sdm_create_voxel_field", "sdm_voxel_field_free", "sdm_refine_voxel_field",
+    "sdm_voxel_field_to_mesh", "sdm_mesh_free", "sdm_field_reset", "sdm_field_upload", "sdm_field_refine", "sdm_field_count",
+    "sdm_field_download", "sdm_field_cases", "sdm_field_to_mesh", "sdm_remesh", "sdm_mesh_download", "sdm_field_triangle_soup",
+    "sdm_field_take_shard", "sdm_get_stats",
+]
+
+
+def lib_path() -> pathlib.Path:
+    return _HERE / "libsdfmesh.so"
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libsdfmesh.so (built in-tree by ``__graft_entry__.build()`` / csrc/Makefile).  Fails loudly."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not p.exists():
+            raise FileNotFoundError(f"{p} is missing - run `python -c 'import __graft_entry__ as g; g.build()'`; there is no CPU fallback")
+        lib = ctypes.CDLL(str(p))
+        lib.sdm_last_error.restype = ctypes.c_char_p
+        lib.sdm_version.restype = ctypes.c_char_p
+        lib.sdm_scene_default.restype = ctypes.c_uint32
+        lib.sdm_destroy.restype = None
+        lib.sdm_voxel_field_free.restype = None
+        lib.sdm_mesh_free.restype = None
+        _lib = lib
+    return _lib
+
+
+@dataclasses.dataclass
+class CudaVoxelField:
+    """``CudaVoxelField`` (src/cuda/mod.rs:42-47): host list of voxel min-corners + the voxel size."""
+
+    voxels: np.ndarray  # (n, 3) float32
+    voxel_size: np.ndarray  # (3,) float32
+
+    def __len__(self) -> int:
+        return int(self.voxels.shape[0])
+
+
+@dataclasses.dataclass
+class Mesh:
+    """What ``voxel_field_to_mesh`` returns, in the layout ``obj_to_bevy_mesh`` consumes (src/renderer/mod.rs:110-128):
+    positions / normals as (V, 3) float32 and a flat triangle-list index buffer as (T, 3) uint32."""
+
+    positions: np.ndarray
+    normals: np.ndarray
+    indices: np.ndarray
+
+    @property
+    def vertex_count(self) -> int:
+        return int(self.positions.shape[0])
+
+    @property
+    def triangle_count(self) -> int:
+        return int(self.indices.shape[0])
+
+
+def _params(bb_size, init_factor, levels=0):
+    return _Params(ctypes.c_float(bb_size), ctypes.c_uint32(init_factor), ctypes.c_uint32(levels))
+
+
+class CudaHandler:
+    BLOCK_SIZE = 128  # bindings.h:7
+    MESH_GENERATION_INIT_FACTOR = 32  # bindings.h:9
+    MESH_GENERATION_BB_SIZE = 5.0  # bindings.h:10
+
+    def __init__(self, device: int = 0, scene: np.ndarray | None = None):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self._check(self._lib.sdm_create(ctypes.c_int(device), ctypes.byref(self._h)))
+        self.device = device
+        if scene is not None:
+            self.set_scene(scene)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise SdfMeshError(rc, self._lib.sdm_last_error().decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.sdm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- scene ------------------------------------------------------------------------------------
+    def set_scene(self, scene: np.ndarray) -> None:
+        scene = np.ascontiguousarray(scene, dtype=PRIM_DTYPE)
+        self._check(self._lib.sdm_set_scene(self._h, scene.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(scene.shape[0])))
+
+    def eval_sdf(self, pts) -> np.ndarray:
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        out = np.empty(pts.shape[0], np.float32)
+        self._check(self._lib.sdm_eval_sdf(self._h, pts.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(pts.shape[0]), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def eval_normal(self, pts) -> np.ndarray:
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        out = np.empty_like(pts)
+        self._check(self._lib.sdm_eval_normal(self._h, pts.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(pts.shape[0]), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def eval_project(self, pts):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        out = np.empty_like(pts)
+        iters = np.empty(pts.shape[0], np.uint32)
+        self._check(self._lib.sdm_eval_project(self._h, pts.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(pts.shape[0]),
+                                               out.ctypes.data_as(ctypes.c_void_p), iters.ctypes.data_as(ctypes.c_void_p)))
+        return out, iters
+
+    # -- the reference's CudaHandler surface (host buffers) -----------------------------------------
+    @staticmethod
+    def create_cuda_voxel_field(bb_size: float = 5.0, init_factor: int = 32) -> CudaVoxelField:
+        lib = load_library()
+        f = _VoxelField()
+        p = _params(bb_size, init_factor)
+        rc = lib.sdm_create_voxel_field(ctypes.byref(p), ctypes.byref(f))
+        if rc:
+            raise SdfMeshError(rc, lib.sdm_last_error().decode())
+        n = int(f.voxel_count)
+        vox = np.ctypeslib.as_array(ctypes.cast(f.voxels, ctypes.POINTER(ctypes.c_float)), shape=(n, 3)).copy()
+        vs = np.array([f.voxel_size.x, f.voxel_size.y, f.voxel_size.z], np.float32)
+        lib.sdm_voxel_field_free(ctypes.byref(f))
+        return CudaVoxelField(vox, vs)
+
+    def _upload(self, field: CudaVoxelField) -> None:
+        vox = np.ascontiguousarray(field.voxels, np.float32).reshape(-1, 3)
+        vs = np.asarray(field.voxel_size, np.float32)
+        f = _VoxelField(_Point(float(vs[0]), float(vs[1]), float(vs[2])), vox.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(vox.shape[0]))
+        self._check(self._lib.sdm_field_upload(self._h, ctypes.byref(f)))
+
+    def refine_voxel_field(self, field: CudaVoxelField) -> None:
+        """In place, like the reference: list replaced by the surviving children, size halved; empty = no-op (:137)."""
+        if len(field) == 0:
+            return
+        self._upload(field)
+        n = self.field_refine()
+        field.voxels = self.field_download(n)
+        field.voxel_size = (np.asarray(field.voxel_size, np.float32) / np.float32(2.0)).astype(np.float32)
+
+    def voxel_field_to_mesh(self, field: CudaVoxelField) -> Mesh:
+        if len(field) == 0:  # :327-345
+            return Mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+        self._upload(field)
+        return self.field_to_mesh()
+
+    # -- device-resident path -----------------------------------------------------------------------
+    def field_reset(self, bb_size: float = 5.0, init_factor: int = 32) -> None:
+        p = _params(bb_size, init_factor)
+        self._check(self._lib.sdm_field_reset(self._h, ctypes.byref(p)))
+
+    def field_upload(self, field: CudaVoxelField) -> None:
+        self._upload(field)
+
+    def field_refine(self) -> int:
+        n = ctypes.c_uint32(0)
+        self._check(self._lib.sdm_field_refine(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def field_count(self):
+        n = ctypes.c_uint32(0)
+        vs = _Point()
+        self._check(self._lib.sdm_field_count(self._h, ctypes.byref(n), ctypes.byref(vs)))
+        return int(n.value), np.array([vs.x, vs.y, vs.z], np.float32)
+
+    def field_download(self, n: int | None = None) -> np.ndarray:
+        if n is None:
+            n, _ = self.field_count()
+        out = np.empty((n, 3), np.float32)
+        self._check(self._lib.sdm_field_download(self._h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(n)))
+        return out
+
+    def field_cases(self) -> np.ndarray:
+        n, _ = self.field_count()
+        out = np.empty(n, np.uint8)
+        self._check(self._lib.sdm_field_cases(self._h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(n)))
+        return out
+
+    def field_triangle_soup(self) -> np.ndarray:
+        """Reference raw format: (5*n, 18) float32 = 5 Triangle slots per voxel (bindings.h:57-64)."""
+        n, _ = self.field_count()
+        out = np.empty((5 * n, 18), np.float32)
+        self._check(self._lib.sdm_field_triangle_soup(self._h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(5 * n)))
+        return out
+
+    def _download(self, m: _Mesh) -> Mesh:
+        pos = np.empty((m.vertex_count, 3), np.float32)
+        nrm = np.empty((m.vertex_count, 3), np.float32)
+        idx = np.empty((m.triangle_count, 3), np.uint32)
+        self._check(self._lib.sdm_mesh_download(self._h, ctypes.byref(m), pos.ctypes.data_as(ctypes.c_void_p),
+                                                nrm.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p)))
+        return Mesh(pos, nrm, idx)
+
+    def field_to_mesh(self, download: bool = True):
+        m = _Mesh()
+        self._check(self._lib.sdm_field_to_mesh(self._h, ctypes.byref(m)))
+        return self._download(m) if download else m
+
+    def remesh(self, bb_size: float = 5.0, init_factor: int = 32, levels: int = 0, download: bool = True):
+        """Level-0 field, ``levels`` refinements and the mesh, all on the device.  With ``download=False`` returns the
+        raw ``SdmMesh`` view (device pointers valid until the next mesh call)."""
+        p = _params(bb_size, init_factor, levels)
+        m = _Mesh()
+        self._check(self._lib.sdm_remesh(self._h, ctypes.byref(p), ctypes.byref(m)))
+        return self._download(m) if download else m
+
+    def stats(self) -> dict:
+        s = _Stats()
+        self._check(self._lib.sdm_get_stats(self._h, ctypes.byref(s)))
+        return dict(kernel_launches=int(s.kernel_launches), sdf_evals=int(s.sdf_evals), level_counts=list(s.level_counts),
+                    unique_vertices=int(s.unique_vertices), raw_triangles=int(s.raw_triangles), last_gpu_ms=float(s.last_gpu_ms))
