@@ -240,3 +240,46 @@ class RefHost:
         return dict(point=L.ref_sizeof_point(), voxel_field=L.ref_sizeof_voxel_field(), voxels_at=L.ref_offsetof_voxels(),
                     count_at=L.ref_offsetof_voxel_count(), vertex=L.ref_sizeof_vertex(), triangle=L.ref_sizeof_triangle(),
                     block_size=L.ref_block_size(), init_factor=L.ref_init_factor(), bb_size=float(L.ref_bb_size()))
+
+
+class RefGpu:
+    """The reference's kernels compiled by nvcc for sm_100a with IEEE flags (oracle/_ref/libref_gpu.so).
+    scene: 0 = unmodified reference kernels (sd_obj), 1 = functor templates with sd_obj, 2 = with sd_unit_mandelbulb."""
+
+    def __init__(self):
+        path = HERE / "_ref" / "libref_gpu.so"
+        if not path.exists():
+            raise FileNotFoundError(str(path))
+        self.lib = ctypes.CDLL(str(path))
+
+    @staticmethod
+    def available() -> bool:
+        return (HERE / "_ref" / "libref_gpu.so").exists()
+
+    def refine_raw(self, scene, vox, vs):
+        vox = np.ascontiguousarray(vox, np.float32).reshape(-1, 3)
+        vs = np.ascontiguousarray(vs, np.float32)
+        out = np.empty((vox.shape[0] * 8, 3), np.float32)
+        rc = self.lib.refgpu_refine(ctypes.c_int(scene), _fp(vox), ctypes.c_uint32(vox.shape[0]), _fp(vs), _fp(out))
+        assert rc == 0
+        return out
+
+    def refine(self, scene, vox, vs):
+        raw = self.refine_raw(scene, vox, vs)
+        keep = np.isfinite(raw).all(axis=1)
+        return raw[keep].copy(), (np.asarray(vs, np.float32) / np.float32(2.0)).astype(np.float32)
+
+    def mesh_raw(self, scene, vox, vs):
+        vox = np.ascontiguousarray(vox, np.float32).reshape(-1, 3)
+        vs = np.ascontiguousarray(vs, np.float32)
+        tris = np.empty((vox.shape[0] * 5, 18), np.float32)
+        rc = self.lib.refgpu_mesh(ctypes.c_int(scene), _fp(vox), ctypes.c_uint32(vox.shape[0]), _fp(vs), _fp(tris))
+        assert rc == 0
+        return tris
+
+    def sdf(self, scene, pts):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        out = np.empty(pts.shape[0], np.float32)
+        rc = self.lib.refgpu_sdf(ctypes.c_int(scene), _fp(pts), ctypes.c_uint32(pts.shape[0]), _fp(out))
+        assert rc == 0
+        return out
