@@ -185,6 +185,9 @@ struct SdmHandle {
     DevBuf<uint64_t> tiles;
     DevBuf<DevState> state;
     DevState* host_state = nullptr;   // pinned
+    DevBuf<uint32_t> shard_range;     // {lo, hi, n} of the last k_take_shard
+    uint32_t* host_range = nullptr;   // pinned
+    uint32_t own_tris = 0, own_uniq = 0;   // the local shard's counts (sdm_shard_remesh)
     uint32_t epoch = 1;
     bool mesh_valid = false;
 
@@ -192,11 +195,44 @@ struct SdmHandle {
     int g_refine = 0, g_classify = 0, g_project = 0, g_normals = 0, g_orient = 0, g_light = 0;
 
     SdmStats stats {};
+
+    // optional per-kernel timing (sdm_set_profiling): one event after every enqueued kernel / clear
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<std::string> prof_names;
+    size_t prof_used = 0;
+    std::vector<float> prof_ms;
 };
 
 namespace {
 
 size_t smem_for(const SdmHandle* h) { return (size_t) h->scene_bytes; }
+
+// profiling: mark(h, name) closes the interval that started at the previous mark
+void prof_begin(SdmHandle* h) {
+    if (!h->profiling) return;
+    h->prof_used = 0;
+    h->prof_names.clear();
+}
+void mark(SdmHandle* h, const char* name) {
+    if (!h->profiling) return;
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_events.push_back(e);
+    }
+    cudaEventRecord(h->prof_events[h->prof_used++], h->stream);
+    h->prof_names.push_back(name);
+}
+void prof_end(SdmHandle* h) {   // after the stream has been synchronised
+    h->prof_ms.clear();
+    if (!h->profiling) return;
+    for (size_t i = 1; i < h->prof_used; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->prof_events[i - 1], h->prof_events[i]);
+        h->prof_ms.push_back(ms);
+    }
+}
 
 int configure_kernels(SdmHandle* h) {
     const size_t smem = smem_for(h);
@@ -272,6 +308,7 @@ int reset_state(SdmHandle* h) {
 int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
     const float size = p.bb_size / (float) p.init_factor;   // src/cuda/mod.rs:106
     k_init_field<<<h->g_light, 256, 0, h->stream>>>(h->vox[0].p, h->state.p, p.bb_size, p.init_factor, size, h->cap_vox);
+    mark(h, "k_init_field");
     h->stats.kernel_launches++;
     h->cur = 0; h->level = 0;
     h->voxel_size[0] = h->voxel_size[1] = h->voxel_size[2] = size;
@@ -285,6 +322,7 @@ int enqueue_refine(SdmHandle* h) {
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
     k_refine<<<h->g_refine, 256, smem_for(h), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
                                                            next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz);
+    mark(h, "k_refine");
     h->stats.kernel_launches++;
     h->cur ^= 1; h->level++;
     h->voxel_size[0] = ox; h->voxel_size[1] = oy; h->voxel_size[2] = oz;
@@ -292,7 +330,17 @@ int enqueue_refine(SdmHandle* h) {
     return SDM_OK;
 }
 
-int enqueue_mesh(SdmHandle* h) {
+int enqueue_weld_clears(SdmHandle* h) {
+    cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(&h->state.p->n_tris_out, 0, 8, s));   // n_tris_out, n_verts_out
+    CK(cudaMemsetAsync(&h->state.p->ticket[TK_SCAN_FIRST], 0, 8, s));
+    CK(cudaMemsetAsync(h->table2.p, 0xFF, (size_t) h->table_entries * 16, s));
+    CK(cudaMemsetAsync(h->first_bits.p, 0, h->first_bits.n * 4, s));
+    return SDM_OK;
+}
+
+// classify -> edges -> project -> normals -> orient: everything that needs only this handle's voxels
+int enqueue_mesh_local(SdmHandle* h) {
     const float sx = h->voxel_size[0], sy = h->voxel_size[1], sz = h->voxel_size[2];
     const float* vox = h->vox[h->cur].p;
     const size_t smem = smem_for(h);
@@ -303,28 +351,54 @@ int enqueue_mesh(SdmHandle* h) {
     CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY), s));
     CK(cudaMemsetAsync(&h->state.p->newton_iters, 0, sizeof(unsigned long long), s));
     CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table_entries * 16, s));
-    CK(cudaMemsetAsync(h->table2.p, 0xFF, (size_t) h->table_entries * 16, s));
     CK(cudaMemsetAsync(h->first_slot.p, 0xFF, (size_t) h->cap_uniq * 4, s));
-    CK(cudaMemsetAsync(h->first_bits.p, 0, h->first_bits.n * 4, s));
+    int rc = enqueue_weld_clears(h);
+    if (rc) return rc;
+    mark(h, "clears");
     k_classify<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cases.p, h->tri_off.p,
                                                  h->cap_tris, sx, sy, sz);
+    mark(h, "k_classify");
     k_edges<<<h->g_light, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, mask, h->ustart.p, h->cap_uniq,
                                         h->slot_ref.p, sx, sy, sz);
+    mark(h, "k_edges");
     k_project<<<h->g_project, 128, smem, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq);
+    mark(h, "k_project");
     k_vertex_normals<<<h->g_normals, 128, smem, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq);
+    mark(h, "k_vertex_normals");
     k_orient<<<h->g_orient, 128, smem, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
                                              h->tri_valid_bits.p);
-    k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, mask, h->wref.p, h->cap_uniq);
-    k_weld_mark<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->cap_uniq);
-    k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_bits.p, h->first_prefix.p, 0, next_epoch(h), h->tiles.p);
-    k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_valid_bits.p, h->tri_prefix.p, 1, next_epoch(h), h->tiles.p);
-    k_emit_vertices<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
-                                                h->upos.p, h->unrm.p, h->out_pos.p, h->out_nrm.p, h->cap_uniq);
-    k_emit_indices<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
-                                               h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx.p);
-    h->stats.kernel_launches += 11;
+    mark(h, "k_orient");
+    h->stats.kernel_launches += 5;
     CK(cudaGetLastError());
     return SDM_OK;
+}
+
+// the reference-order weld over (upos, unrm, tri_uid, first_slot, tri_valid_bits) and the counters in DevState
+int enqueue_weld(SdmHandle* h) {
+    cudaStream_t s = h->stream;
+    const uint32_t mask = h->table_entries - 1;
+    k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, mask, h->wref.p, h->cap_uniq);
+    mark(h, "k_weld_insert");
+    k_weld_mark<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->cap_uniq);
+    mark(h, "k_weld_mark");
+    k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_bits.p, h->first_prefix.p, 0, next_epoch(h), h->tiles.p);
+    k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_valid_bits.p, h->tri_prefix.p, 1, next_epoch(h), h->tiles.p);
+    mark(h, "k_bitscan_x2");
+    k_emit_vertices<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
+                                                h->upos.p, h->unrm.p, h->out_pos.p, h->out_nrm.p, h->cap_uniq);
+    mark(h, "k_emit_vertices");
+    k_emit_indices<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
+                                               h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx.p);
+    mark(h, "k_emit_indices");
+    h->stats.kernel_launches += 6;
+    CK(cudaGetLastError());
+    return SDM_OK;
+}
+
+int enqueue_mesh(SdmHandle* h) {
+    int rc = enqueue_mesh_local(h);
+    if (rc) return rc;
+    return enqueue_weld(h);
 }
 
 // Copies DevState to the pinned host mirror and waits.  Returns the device-side error flags through *flags.
@@ -422,6 +496,9 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
         if (cudaMallocHost(&h->host_state, sizeof(DevState)) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMallocHost"); break; }
         memset(h->host_state, 0, sizeof(DevState));
+        if (cudaMallocHost(&h->host_range, 16) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMallocHost"); break; }
+        memset(h->host_range, 0, 16);
+        if (h->shard_range.reserve(4) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc range"); break; }
         if (h->state.reserve(1) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc state"); break; }
         cudaMemsetAsync(h->state.p, 0, sizeof(DevState), h->stream);
         cudaMemcpyToSymbolAsync(c_mc_packed, SDM_MC_PACKED_INIT, sizeof(SDM_MC_PACKED_INIT), 0, cudaMemcpyHostToDevice, h->stream);
@@ -448,6 +525,9 @@ void sdm_destroy(SdmHandle* h) {
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->out_idx.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     h->out_pos.release(); h->out_nrm.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
+    if (h->host_range) cudaFreeHost(h->host_range);
+    h->shard_range.release();
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -677,9 +757,11 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
     for (int attempt = 0; attempt < 10; attempt++) {
         rc = ensure_capacity(h, want);
         if (rc) return rc;
+        prof_begin(h);
         CK(cudaEventRecord(h->ev0, h->stream));
         rc = reset_state(h);
         if (rc) return rc;
+        mark(h, "start");
         rc = enqueue_init_field(h, p);
         if (rc) return rc;
         for (uint32_t l = 0; l < p.levels; l++) {
@@ -698,6 +780,7 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
             h->stats.last_gpu_ms = ms;
             h->mesh_valid = true;
             fill_stats(h, true);
+            prof_end(h);
             mesh_view(h, out_mesh);
             return SDM_OK;
         }
@@ -760,9 +843,160 @@ void sdm_mesh_free(SdmMesh* mesh) {
     memset(mesh, 0, sizeof(*mesh));
 }
 
-int sdm_field_take_shard(SdmHandle* h, uint32_t shard_index, uint32_t shard_count) {
-    (void) h; (void) shard_index; (void) shard_count;
-    return fail(SDM_ERR_STATE, "sdm_field_take_shard: not implemented yet");
+// ---- shards ----------------------------------------------------------------------------------------------
+int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level, uint32_t shard_index, uint32_t shard_count,
+                     SdmShardInfo* out_info) {
+    if (!h || !out_info) return fail(SDM_ERR_INVALID, "null argument");
+    SdmParams p { SDM_MESH_GENERATION_BB_SIZE, SDM_MESH_GENERATION_INIT_FACTOR, 0 };
+    if (params) p = *params;
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (shard_count == 0 || shard_index >= shard_count) return fail(SDM_ERR_INVALID, "bad shard index / count");
+    if (split_level > p.levels) split_level = p.levels;
+    CK(cudaSetDevice(h->device));
+    uint32_t want = h->cap_vox;
+    const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
+    while (want < n0) want = grown(want);
+    for (int attempt = 0; attempt < 10; attempt++) {
+        rc = ensure_capacity(h, want);
+        if (rc) return rc;
+        prof_begin(h);
+        CK(cudaEventRecord(h->ev0, h->stream));
+        rc = reset_state(h);
+        if (rc) return rc;
+        mark(h, "start");
+        rc = enqueue_init_field(h, p);
+        if (rc) return rc;
+        for (uint32_t l = 0; l < split_level; l++) {   // redundantly on every rank: the coarse levels are tiny
+            rc = enqueue_refine(h);
+            if (rc) return rc;
+        }
+        k_take_shard<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, shard_index, shard_count,
+                                                         h->shard_range.p);
+        k_set_level_count<<<1, 1, 0, h->stream>>>(h->state.p, h->level, h->shard_range.p);
+        mark(h, "k_take_shard");
+        h->stats.kernel_launches += 2;
+        h->cur ^= 1;
+        for (uint32_t l = split_level; l < p.levels; l++) {
+            rc = enqueue_refine(h);
+            if (rc) return rc;
+        }
+        rc = enqueue_mesh_local(h);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaMemcpyAsync(h->host_range, h->shard_range.p, 12, cudaMemcpyDeviceToHost, h->stream));
+        uint32_t flags = 0;
+        rc = fetch_state(h, &flags);
+        if (rc) return rc;
+        if (!flags) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            h->stats.last_gpu_ms = ms;
+            h->mesh_valid = false;   // no welded mesh yet
+            fill_stats(h, true);
+            prof_end(h);
+            h->own_tris = h->host_state->n_tris_raw;
+            h->own_uniq = h->host_state->n_uniq;
+            out_info->shard_index = shard_index; out_info->shard_count = shard_count; out_info->split_level = split_level;
+            out_info->voxel_begin = h->host_range[0]; out_info->voxel_end = h->host_range[1]; out_info->split_total = h->host_range[2];
+            out_info->final_voxels = h->host_state->level_count[h->level];
+            out_info->unique_vertices = h->own_uniq; out_info->raw_triangles = h->own_tris;
+            return SDM_OK;
+        }
+        want = grown(h->cap_vox);
+        if (want == h->cap_vox) break;
+    }
+    return fail(SDM_ERR_CAPACITY, "shard does not fit in device memory");
+}
+
+int sdm_shard_buffers(SdmHandle* h, SdmShardBuffers* out) {
+    if (!h || !out) return fail(SDM_ERR_INVALID, "null argument");
+    out->positions = h->upos.p; out->normals = h->unrm.p; out->triangle_vertex_ids = h->tri_uid.p;
+    out->capacity_vertices = h->cap_uniq; out->capacity_triangles = h->cap_tris;
+    return SDM_OK;
+}
+
+int sdm_shard_prepare_send(SdmHandle* h, uint32_t vertex_offset) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    k_shard_prepare_send<<<h->g_light, 256, 0, h->stream>>>(h->state.p, h->tri_uid.p, h->tri_valid_bits.p, vertex_offset);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));   // the buffers are handed to NCCL on another stream next
+    return SDM_OK;
+}
+
+int sdm_shard_reserve(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    uint32_t want = h->cap_vox;
+    while ((uint64_t) want * 2 < total_vertices || (uint64_t) want * 3 < total_triangles) {
+        const uint32_t g = grown(want);
+        if (g == want) return fail(SDM_ERR_CAPACITY, "merged mesh too large");
+        want = g;
+    }
+    if (want == h->cap_vox) return SDM_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    // keep the local shard's vertices / triangles: detach, re-allocate everything, copy back
+    float* old_pos = h->upos.p; float* old_nrm = h->unrm.p; uint32_t* old_uid = h->tri_uid.p; uint32_t* old_bits = h->tri_valid_bits.p;
+    h->upos.p = nullptr; h->upos.n = 0; h->unrm.p = nullptr; h->unrm.n = 0; h->tri_uid.p = nullptr; h->tri_uid.n = 0;
+    h->tri_valid_bits.p = nullptr; h->tri_valid_bits.n = 0;
+    int rc = ensure_capacity(h, want);
+    if (rc == SDM_OK) {
+        cudaMemcpyAsync(h->upos.p, old_pos, (size_t) h->own_uniq * 12, cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->unrm.p, old_nrm, (size_t) h->own_uniq * 12, cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->tri_uid.p, old_uid, (size_t) h->own_tris * 12, cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->tri_valid_bits.p, old_bits, ((size_t) h->own_tris + 31) / 32 * 4, cudaMemcpyDeviceToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(old_pos); cudaFree(old_nrm); cudaFree(old_uid); cudaFree(old_bits);
+    return rc;
+}
+
+int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh) {
+    if (!h || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
+    if (total_vertices > h->cap_uniq || total_triangles > h->cap_tris) return fail(SDM_ERR_CAPACITY, "call sdm_shard_reserve first");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CK(cudaEventRecord(h->ev0, s));
+    h->host_range[3] = 0;
+    uint32_t* counts = h->host_range;   // pinned scratch: {n_tris_raw, n_uniq}
+    counts[0] = total_triangles; counts[1] = total_vertices;
+    CK(cudaMemcpyAsync(&h->state.p->n_tris_raw, counts, 8, cudaMemcpyHostToDevice, s));   // n_tris_raw, n_uniq are adjacent
+    int rc = enqueue_weld_clears(h);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->first_slot.p, 0xFF, (size_t) total_vertices * 4, s));
+    k_first_slot_merged<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->first_slot.p, h->tri_valid_bits.p, h->own_tris);
+    h->stats.kernel_launches++;
+    rc = enqueue_weld(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev1, s));
+    uint32_t flags = 0;
+    rc = fetch_state(h, &flags);
+    if (rc) return rc;
+    if (flags) return fail(SDM_ERR_CAPACITY, "weld table overflow");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_gpu_ms = ms;
+    mesh_view(h, out_mesh);
+    return SDM_OK;
+}
+
+int sdm_set_profiling(SdmHandle* h, int enabled) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    h->profiling = enabled != 0;
+    return SDM_OK;
+}
+// Per-kernel CUDA-event times (ms) of the last sdm_remesh, in launch order.  Returns the number of entries;
+// names[i] points into storage owned by the handle (valid until the next remesh).
+int sdm_get_kernel_times(SdmHandle* h, const char** names, float* ms, uint32_t capacity) {
+    if (!h) return 0;
+    const size_t n = std::min<size_t>(h->prof_ms.size(), capacity);
+    for (size_t i = 0; i < n; i++) {
+        if (names) names[i] = h->prof_names[i + 1].c_str();
+        if (ms) ms[i] = h->prof_ms[i];
+    }
+    return (int) n;
 }
 
 int sdm_get_stats(SdmHandle* h, SdmStats* out) {

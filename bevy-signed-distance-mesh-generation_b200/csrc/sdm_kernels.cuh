@@ -17,10 +17,14 @@
 // device memory, so that a whole remesh is enqueued without any host synchronisation.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "sdm_device.cuh"
 #include "mc_tables.inc"
 
 namespace sdm {
+
+namespace cg = cooperative_groups;
 
 enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_COUNT = 24 };
 enum ErrFlag : uint32_t {
@@ -280,7 +284,11 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
                 const uint32_t pos = hash_find_or_insert(table, table_mask, kx, ky, kz, 0xFFFFFFFEu, &won);
                 if (pos == 0xFFFFFFFFu) { atomicOr(&st->error_flags, ERR_HASH_FULL); continue; }
                 if (won) {
-                    const uint32_t uid = atomicAdd(&st->n_uniq, 1u);
+                    // warp-aggregated allocation: one atomic per group of winning lanes, not one per vertex
+                    const cg::coalesced_group g = cg::coalesced_threads();
+                    uint32_t base = 0;
+                    if (g.thread_rank() == 0) base = atomicAdd(&st->n_uniq, (uint32_t) g.size());
+                    const uint32_t uid = g.shfl(base, 0) + g.thread_rank();
                     if (uid < cap_uniq) {
                         ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
                     } else {
@@ -543,6 +551,58 @@ __global__ void __launch_bounds__(256) k_soup(DevState* st, int level, const uin
                 for (int q = 0; q < 18; q++) o[t * 18 + q] = q < 6 ? __int_as_float(0x7fc00000) : 0.0f;
             }
         }
+    }
+}
+
+// ---- shards (multi-GPU) ----------------------------------------------------------------------------------
+// Restrict the list of `level` to the contiguous part [n*shard/count, n*(shard+1)/count) (64-bit arithmetic),
+// copied to the front of the other ping-pong buffer.  Children keep their parent's order (compute_mesh_generation.cu:51)
+// and level 0 is x-major (src/cuda/mod.rs:110-119), so a contiguous part of the list is an x-slab at every level.
+__global__ void __launch_bounds__(256) k_take_shard(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
+                                                    uint32_t shard, uint32_t count, uint32_t* __restrict__ range_out) {
+    const uint32_t n = st->level_count[level];
+    const uint32_t lo = (uint32_t) ((uint64_t) n * shard / count), hi = (uint32_t) ((uint64_t) n * (shard + 1) / count);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * (hi - lo); i += gridDim.x * blockDim.x) out_vox[i] = in_vox[3 * (size_t) lo + i];
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { range_out[0] = lo; range_out[1] = hi; range_out[2] = n; }
+}
+// all blocks must have read level_count before it is overwritten: done by a second, tiny launch
+__global__ void k_set_level_count(DevState* st, int level, const uint32_t* __restrict__ range) { st->level_count[level] = range[1] - range[0]; }
+
+// Sender side of the gather: vertex ids become global (offset of this shard's vertices in the merged table) and a
+// triangle dropped by the finite filter is marked with id 0xFFFFFFFF in its first slot.
+__global__ void __launch_bounds__(256) k_shard_prepare_send(DevState* st, uint32_t* __restrict__ tri_uid, const uint32_t* __restrict__ tri_valid_bits,
+                                                            uint32_t vertex_offset) {
+    const uint32_t T = st->n_tris_raw;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        const bool valid = (tri_valid_bits[t >> 5] >> (t & 31u)) & 1u;
+        tri_uid[3 * (size_t) t] = valid ? tri_uid[3 * (size_t) t] + vertex_offset : 0xFFFFFFFFu;
+        tri_uid[3 * (size_t) t + 1] += vertex_offset;
+        tri_uid[3 * (size_t) t + 2] += vertex_offset;
+    }
+}
+// Root side: first-occurrence slots and validity bits over the merged triangle list (what k_orient does for one shard).
+__global__ void __launch_bounds__(256) k_first_slot_merged(DevState* st, uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
+                                                           uint32_t* __restrict__ tri_valid_bits, uint32_t own_tris) {
+    const uint32_t T = st->n_tris_raw;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t t0 = warp_id << 5; t0 < T; t0 += warps_total << 5) {
+        const uint32_t t = t0 + lane;
+        bool valid = false;
+        if (t < T) {
+            const uint32_t u0 = tri_uid[3 * (size_t) t];
+            // the root's own triangles (t < own_tris) still carry their local validity bits, not the marker
+            valid = t < own_tris ? ((tri_valid_bits[t >> 5] >> (t & 31u)) & 1u) : (u0 != 0xFFFFFFFFu);
+            if (valid) {
+                atomicMin(first_slot + u0, 3u * t);
+                atomicMin(first_slot + tri_uid[3 * (size_t) t + 1], 3u * t + 1u);
+                atomicMin(first_slot + tri_uid[3 * (size_t) t + 2], 3u * t + 2u);
+            }
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) tri_valid_bits[t0 >> 5] = bits;
     }
 }
 

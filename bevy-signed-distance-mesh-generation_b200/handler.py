@@ -61,6 +61,16 @@ class _Stats(ctypes.Structure):
     ]
 
 
+class _ShardInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("shard_index", "shard_count", "split_level", "split_total", "voxel_begin", "voxel_end",
+                                               "final_voxels", "unique_vertices", "raw_triangles")]
+
+
+class _ShardBuffers(ctypes.Structure):
+    _fields_ = [("positions", ctypes.c_void_p), ("normals", ctypes.c_void_p), ("triangle_vertex_ids", ctypes.c_void_p),
+                ("capacity_vertices", ctypes.c_uint32), ("capacity_triangles", ctypes.c_uint32)]
+
+
 assert ctypes.sizeof(_VoxelField) == 32 and _VoxelField.voxels.offset == 16 and _VoxelField.voxel_count.offset == 24
 
 # every symbol include/sdfmesh.h declares (tests/test_abi.py checks the library exports each one)
@@ -69,7 +79,8 @@ ABI_SYMBOLS = [
     "sdm_eval_normal", "sdm_eval_project", "sdm_create_voxel_field", "sdm_voxel_field_free", "sdm_refine_voxel_field",
     "sdm_voxel_field_to_mesh", "sdm_mesh_free", "sdm_field_reset", "sdm_field_upload", "sdm_field_refine", "sdm_field_count",
     "sdm_field_download", "sdm_field_cases", "sdm_field_to_mesh", "sdm_remesh", "sdm_mesh_download", "sdm_field_triangle_soup",
-    "sdm_field_take_shard", "sdm_get_stats",
+    "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
+    "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times",
 ]
 
 
@@ -286,6 +297,46 @@ class CudaHandler:
         m = _Mesh()
         self._check(self._lib.sdm_remesh(self._h, ctypes.byref(p), ctypes.byref(m)))
         return self._download(m) if download else m
+
+    # -- shards (multi-GPU) -------------------------------------------------------------------------
+    def shard_remesh(self, bb_size, init_factor, levels, split_level, shard_index, shard_count) -> dict:
+        p = _params(bb_size, init_factor, levels)
+        info = _ShardInfo()
+        self._check(self._lib.sdm_shard_remesh(self._h, ctypes.byref(p), ctypes.c_uint32(split_level), ctypes.c_uint32(shard_index),
+                                               ctypes.c_uint32(shard_count), ctypes.byref(info)))
+        return {n: int(getattr(info, n)) for n, _ in _ShardInfo._fields_}
+
+    def shard_buffers(self) -> dict:
+        b = _ShardBuffers()
+        self._check(self._lib.sdm_shard_buffers(self._h, ctypes.byref(b)))
+        return dict(positions=int(b.positions or 0), normals=int(b.normals or 0), triangle_vertex_ids=int(b.triangle_vertex_ids or 0),
+                    capacity_vertices=int(b.capacity_vertices), capacity_triangles=int(b.capacity_triangles))
+
+    def shard_prepare_send(self, vertex_offset: int) -> None:
+        self._check(self._lib.sdm_shard_prepare_send(self._h, ctypes.c_uint32(vertex_offset)))
+
+    def shard_reserve(self, total_vertices: int, total_triangles: int) -> None:
+        self._check(self._lib.sdm_shard_reserve(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles)))
+
+    def shard_weld(self, total_vertices: int, total_triangles: int, download: bool = False):
+        m = _Mesh()
+        self._check(self._lib.sdm_shard_weld(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles), ctypes.byref(m)))
+        return self._download(m) if download else m
+
+    def download_into(self, m, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:
+        """sdm_mesh_download into caller-provided (e.g. pinned) host memory."""
+        self._check(self._lib.sdm_mesh_download(self._h, ctypes.byref(m), ctypes.c_void_p(positions_ptr), ctypes.c_void_p(normals_ptr),
+                                                ctypes.c_void_p(indices_ptr)))
+
+    def set_profiling(self, enabled: bool) -> None:
+        self._check(self._lib.sdm_set_profiling(self._h, ctypes.c_int(1 if enabled else 0)))
+
+    def kernel_times(self):
+        """[(kernel name, ms)] of the last remesh (needs set_profiling(True))."""
+        names = (ctypes.c_char_p * 64)()
+        ms = (ctypes.c_float * 64)()
+        n = self._lib.sdm_get_kernel_times(self._h, names, ms, ctypes.c_uint32(64))
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def stats(self) -> dict:
         s = _Stats()

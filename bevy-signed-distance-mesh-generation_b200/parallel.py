@@ -1,0 +1,152 @@
+"""Multi-GPU remesh: contiguous shards of the active list, one process / handle per GPU, mesh shards gathered to
+rank 0 over NVLink with NCCL (torch.distributed), welded there into exactly the single-GPU mesh.
+
+Why this shape: every voxel's classification, vertices and normals depend only on its own corner
+coordinates and the analytic SDF (compute_mesh_generation.cu:27-58, 74-86) - no halo is needed - and the list is
+x-major with children in parent order, so a contiguous part of the list is an x-slab at every level.  Only the weld
+(global first-occurrence order, src/cuda/mod.rs:263-296) needs all shards: it is the one exchange step.
+
+`plan_offsets` and `merge_counts` are pure host logic (tested with gloo on CPU, world size 2); the transport uses
+zero-copy torch views of the library's device buffers.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+
+def shard_range(n: int, shard: int, count: int):
+    """The contiguous part of an n-voxel list owned by `shard` (same arithmetic as k_take_shard)."""
+    return (n * shard) // count, (n * (shard + 1)) // count
+
+
+def plan_offsets(counts):
+    """counts: [(unique_vertices, raw_triangles)] per rank, in rank order -> (vertex_offsets, triangle_offsets, totals)."""
+    v_off, t_off = [], []
+    v = t = 0
+    for u, tr in counts:
+        v_off.append(v)
+        t_off.append(t)
+        v += int(u)
+        t += int(tr)
+    return v_off, t_off, (v, t)
+
+
+def choose_split_level(init_factor: int, levels: int, world: int) -> int:
+    """Coarse levels are refined redundantly on every rank; the split happens once the list is long enough that an
+    equal-count split is also a balanced split of the final work (>= ~64 voxels per rank per SM is plenty), and
+    never later than level 2 so that the redundant part stays negligible."""
+    if world <= 1:
+        return 0
+    return min(levels, 1 if init_factor >= 64 else 2)
+
+
+class _DevView:
+    """Zero-copy view of library-owned device memory for torch (``torch.as_tensor(view, device='cuda')``)."""
+
+    def __init__(self, ptr: int, nelem: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _view(torch, ptr, nelem, typestr, device):
+    if nelem == 0:
+        return torch.empty(0, dtype=torch.float32 if typestr == "<f4" else torch.int32, device=device)
+    return torch.as_tensor(_DevView(ptr, nelem, typestr), device=device)
+
+
+class ShardedRemesher:
+    """step() = one full remesh on `world` GPUs; on rank 0 the welded mesh is left in HBM."""
+
+    def __init__(self, handler, bb_size, init_factor, levels, rank=0, world=1, dist=None):
+        self.h, self.bb, self.init, self.levels = handler, bb_size, init_factor, levels
+        self.rank, self.world, self.dist = rank, world, dist
+        self.split_level = choose_split_level(init_factor, levels, world)
+        self.last_gpu_ms = 0.0
+        self.mesh = None
+        self._pinned = None
+
+    # -- single GPU: the fused device-resident path -------------------------------------------------
+    def _step_single(self):
+        m = self.h.remesh(self.bb, self.init, self.levels, download=False)
+        self.last_gpu_ms = self.h.stats()["last_gpu_ms"]
+        self.mesh = m
+        return {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
+
+    # -- N GPUs ---------------------------------------------------------------------------------------
+    def _step_sharded(self):
+        import torch
+
+        dist, h = self.dist, self.h
+        dev = torch.device("cuda", torch.cuda.current_device())
+        info = h.shard_remesh(self.bb, self.init, self.levels, self.split_level, self.rank, self.world)
+        gpu_ms = h.stats()["last_gpu_ms"]
+        mine = torch.tensor([info["unique_vertices"], info["raw_triangles"]], dtype=torch.int64, device=dev)
+        allc = torch.empty((self.world, 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        counts = [(int(a), int(b)) for a, b in allc.cpu().tolist()]
+        v_off, t_off, (V, T) = plan_offsets(counts)
+        ops = []
+        if self.rank == 0:
+            h.shard_reserve(V, T)
+            b = h.shard_buffers()
+            for r in range(1, self.world):
+                u, tr = counts[r]
+                if u:
+                    ops.append(dist.P2POp(dist.irecv, _view(torch, b["positions"] + 12 * v_off[r], 3 * u, "<f4", dev), r))
+                    ops.append(dist.P2POp(dist.irecv, _view(torch, b["normals"] + 12 * v_off[r], 3 * u, "<f4", dev), r))
+                if tr:
+                    ops.append(dist.P2POp(dist.irecv, _view(torch, b["triangle_vertex_ids"] + 12 * t_off[r], 3 * tr, "<i4", dev), r))
+        else:
+            h.shard_prepare_send(v_off[self.rank])
+            b = h.shard_buffers()
+            u, tr = counts[self.rank]
+            if u:
+                ops.append(dist.P2POp(dist.isend, _view(torch, b["positions"], 3 * u, "<f4", dev), 0))
+                ops.append(dist.P2POp(dist.isend, _view(torch, b["normals"], 3 * u, "<f4", dev), 0))
+            if tr:
+                ops.append(dist.P2POp(dist.isend, _view(torch, b["triangle_vertex_ids"], 3 * tr, "<i4", dev), 0))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        torch.cuda.current_stream().synchronize()
+        out = {"triangles": 0, "vertices": 0}
+        if self.rank == 0:
+            m = h.shard_weld(V, T)
+            gpu_ms += h.stats()["last_gpu_ms"]
+            self.mesh = m
+            out = {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
+        self.last_gpu_ms = gpu_ms
+        return out
+
+    def step(self):
+        return self._step_single() if self.world == 1 else self._step_sharded()
+
+    # -- end-to-end arm: host scene in, pinned host mesh out, every step -----------------------------------
+    def e2e(self, scene, steps, warmup, barrier):
+        import torch
+
+        h = self.h
+        scene = np.ascontiguousarray(scene)
+        h2d = int(scene.nbytes)
+        d2h = 0
+        pos = nrm = idx = None
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(warmup + steps):
+            if i == warmup:
+                barrier()
+                t0 = time.perf_counter()
+            h.set_scene(scene)                 # host -> device: the scene table (the path's only input)
+            out = self.step()
+            if self.rank == 0:
+                m = self.mesh
+                need_v, need_t = int(m.vertex_count), int(m.triangle_count)
+                if pos is None or pos.shape[0] < need_v or idx.shape[0] < need_t:
+                    pos = torch.empty((max(need_v, 1), 3), dtype=torch.float32).pin_memory()
+                    nrm = torch.empty((max(need_v, 1), 3), dtype=torch.float32).pin_memory()
+                    idx = torch.empty((max(need_t, 1), 3), dtype=torch.int32).pin_memory()
+                h.download_into(m, pos.data_ptr(), nrm.data_ptr(), idx.data_ptr())   # device -> host: the mesh
+                d2h = need_v * 24 + need_t * 12
+        barrier()
+        return {"elapsed": time.perf_counter() - t0, "h2d": h2d, "d2h": d2h}

@@ -155,11 +155,40 @@ int sdm_mesh_download(SdmHandle* h, const SdmMesh* device_mesh, float* positions
  * (compute_mesh_generation.cu:64-120), to host (capacity in triangles, >= 5 * voxel_count). */
 int sdm_field_triangle_soup(SdmHandle* h, SdmTriangle* out_triangles, uint32_t capacity);
 
-/* ---- shards (multi-GPU: contiguous ranges of the level-`split_level` active list) --------------- */
-/* Restrict the device field to the [shard_index/shard_count) contiguous part of the current list,
- * balanced by voxel count.  Global slot ids are preserved through sdm_shard_info so that per-shard
- * meshes can be merged into exactly the single-GPU mesh. */
-int sdm_field_take_shard(SdmHandle* h, uint32_t shard_index, uint32_t shard_count);
+/* ---- shards (multi-GPU: one process and one handle per GPU) -------------------------------------------------------
+ * Every voxel is classified, projected and oriented from its own corner coordinates and the analytic SDF, so a
+ * contiguous part of the active list can be meshed with no halo; only the weld (global first-occurrence vertex
+ * order, src/cuda/mod.rs:263-296) needs all shards.  Flow per remesh:
+ *   every rank : sdm_shard_remesh   - levels [0, split_level) redundantly, then its contiguous part of the
+ *                                     level-`split_level` list refined to full depth and meshed up to (not incl.) the weld
+ *   ranks > 0  : sdm_shard_prepare_send(vertex_offset) - make vertex ids global, mark dropped triangles
+ *   transport  : positions / normals / triangle_vertex_ids (sdm_shard_buffers) are sent to rank 0 at the offsets
+ *                given by the exclusive sums of the shards' counts (NCCL send/recv over NVLink; the Python host in
+ *                bevy-signed-distance-mesh-generation_b200/parallel.py does this with torch.distributed)
+ *   rank 0     : sdm_shard_reserve(totals) before receiving, sdm_shard_weld(totals) after: the merged mesh is
+ *                byte-identical to the single-GPU mesh.
+ */
+typedef struct SdmShardInfo {
+    uint32_t shard_index, shard_count, split_level;
+    uint32_t split_total;            /* voxels in the level-`split_level` list */
+    uint32_t voxel_begin, voxel_end; /* this shard's part of that list */
+    uint32_t final_voxels;           /* this shard's voxels at the finest level */
+    uint32_t unique_vertices;        /* rows of positions / normals */
+    uint32_t raw_triangles;          /* rows of triangle_vertex_ids */
+} SdmShardInfo;
+typedef struct SdmShardBuffers {     /* device memory owned by the handle */
+    float* positions;                /* [capacity_vertices][3] */
+    float* normals;                  /* [capacity_vertices][3] */
+    uint32_t* triangle_vertex_ids;   /* [capacity_triangles][3], post-flip order */
+    uint32_t capacity_vertices, capacity_triangles;
+} SdmShardBuffers;
+int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level, uint32_t shard_index, uint32_t shard_count,
+                     SdmShardInfo* out_info);
+int sdm_shard_buffers(SdmHandle* h, SdmShardBuffers* out);
+int sdm_shard_prepare_send(SdmHandle* h, uint32_t vertex_offset);
+/* Grows the handle's buffers to hold the merged mesh, preserving the local shard's rows. */
+int sdm_shard_reserve(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles);
+int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh);
 
 /* ---- counters for the bench ------------------------------------------------------------------------ */
 typedef struct SdmStats {
@@ -172,6 +201,10 @@ typedef struct SdmStats {
     uint32_t reserved;
 } SdmStats;
 int sdm_get_stats(SdmHandle* h, SdmStats* out);
+/* Per-kernel timing for the bench's roofline line: when enabled, sdm_remesh records a CUDA event on the handle's
+ * stream after every kernel it enqueues; sdm_get_kernel_times returns (name, ms) per kernel of the last remesh. */
+int sdm_set_profiling(SdmHandle* h, int enabled);
+int sdm_get_kernel_times(SdmHandle* h, const char** names, float* ms, uint32_t capacity);
 
 #ifdef __cplusplus
 }
