@@ -89,6 +89,7 @@ int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>&
     for (uint32_t i = 0; i < count; i++) {
         const SdmPrimitive& q = prims[i];
         if (q.fold != SDM_FOLD_MIN && q.fold != SDM_FOLD_SMOOTH_MIN) return fail(SDM_ERR_INVALID, "unknown fold op");
+        if (q.fold == SDM_FOLD_SMOOTH_MIN && !(q.k > 0.0f)) return fail(SDM_ERR_INVALID, "smooth_min needs k > 0");
         const H3 a { q.a[0], q.a[1], q.a[2] }, b { q.b[0], q.b[1], q.b[2] };
         DevPrim d;
         memset(&d, 0, sizeof(d));
@@ -167,6 +168,12 @@ struct SdmHandle {
     // scene
     DevBuf<uint4> scene;
     uint32_t scene_bytes = 0;
+    uint32_t scene_nprims = 0;          // compiled primitives (skeletons expanded)
+    bool mask_capable = false;          // large scene of 1-Lipschitz primitives: per-cell primitive masks are used
+    DevBuf<uint32_t> masks_fine, masks_coarse;
+    MaskGrid grid {};                   // grid.enabled == 0 until ensure_masks has built it
+    float grid_bb = 0.0f;
+    uint32_t masks_built = 0;           // statistics: number of mask builds
 
     // field (ping-pong lists) and its host-known description
     DevBuf<float> vox[2];
@@ -206,7 +213,12 @@ struct SdmHandle {
 
 namespace {
 
-size_t smem_for(const SdmHandle* h) { return (size_t) h->scene_bytes; }
+// dynamic shared memory: the scene blob, then one primitive mask per warp when culling is on
+size_t smem_for(const SdmHandle* h, int threads = 256) {
+    size_t b = (size_t) h->scene_bytes;
+    if (h->mask_capable) b += (size_t) (threads / 32) * ((h->scene_nprims + 31) / 32) * 4;
+    return (b + 15) & ~(size_t) 15;
+}
 
 // profiling: mark(h, name) closes the interval that started at the previous mark
 void prof_begin(SdmHandle* h) {
@@ -235,8 +247,7 @@ void prof_end(SdmHandle* h) {   // after the stream has been synchronised
 }
 
 int configure_kernels(SdmHandle* h) {
-    const size_t smem = smem_for(h);
-    if (smem > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
+    if (smem_for(h, 256) > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
     struct K { const void* f; int threads; int* grid; };
     const K ks[] = {
         { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify, 256, &h->g_classify },
@@ -244,6 +255,7 @@ int configure_kernels(SdmHandle* h) {
         { (const void*) k_orient, 128, &h->g_orient },
     };
     for (const K& k : ks) {
+        const size_t smem = smem_for(h, k.threads);
         CK(cudaFuncSetAttribute(k.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.f, k.threads, smem));
@@ -251,8 +263,41 @@ int configure_kernels(SdmHandle* h) {
         *k.grid = per_sm * h->num_sms;
     }
     for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project })
-        CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
+        CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 128), 1024)));
+    CK(cudaFuncSetAttribute((const void*) k_build_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 256), 1024)));
     h->g_light = h->num_sms * 8;
+    return SDM_OK;
+}
+
+// Per-cell primitive masks over the cube [-bb/2, bb/2]^3 (two levels: G/4 coarse cells prune for the G fine cells).
+int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
+    if (!h->mask_capable) { h->grid.enabled = 0; return SDM_OK; }
+    const uint32_t W = (h->scene_nprims + 31) / 32;
+    uint32_t G = 16;
+    while (G < init_factor && G < 128) G <<= 1;
+    if (W > 32 && G > 64) G = 64;
+    if (h->grid.enabled && h->grid.G == G && h->grid_bb == bb_size) return SDM_OK;
+    const uint32_t Gc = G / 4;
+    CK(h->masks_fine.reserve((size_t) G * G * G * W));
+    CK(h->masks_coarse.reserve((size_t) Gc * Gc * Gc * W));
+    MaskGrid fine {};
+    fine.masks = h->masks_fine.p; fine.G = G; fine.W = W;
+    fine.ox = fine.oy = fine.oz = -bb_size / 2.0f;
+    fine.cell = bb_size / (float) G; fine.inv_cell = (float) G / bb_size; fine.enabled = 1;
+    MaskGrid coarse = fine;
+    coarse.masks = h->masks_coarse.p; coarse.G = Gc; coarse.cell = bb_size / (float) Gc; coarse.inv_cell = (float) Gc / bb_size;
+    // radius = circumsphere of the cell cube (x1.0001) + the empirical_normal stencil reach (2e-3, signed_distance.cu:179)
+    //          + slop for the inward-nudged box probes and the domain-face tolerance (2e-3 cell) + 1e-4
+    auto rho = [](float cell) { return cell * 0.8660254f * 1.0001f + 0.0021f + 2e-3f * cell + 1e-4f; };
+    const size_t smem = smem_for(h, 256);
+    k_build_masks<<<h->num_sms * 4, 256, smem, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell));
+    k_build_masks<<<h->num_sms * 8, 256, smem, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell));
+    mark(h, "k_build_masks_x2");
+    h->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    h->grid = fine;
+    h->grid_bb = bb_size;
+    h->masks_built++;
     return SDM_OK;
 }
 
@@ -306,6 +351,8 @@ int reset_state(SdmHandle* h) {
 }
 
 int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
+    int mrc = ensure_masks(h, p.bb_size, p.init_factor);
+    if (mrc) return mrc;
     const float size = p.bb_size / (float) p.init_factor;   // src/cuda/mod.rs:106
     k_init_field<<<h->g_light, 256, 0, h->stream>>>(h->vox[0].p, h->state.p, p.bb_size, p.init_factor, size, h->cap_vox);
     mark(h, "k_init_field");
@@ -320,8 +367,8 @@ int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
 int enqueue_refine(SdmHandle* h) {
     if (h->level >= 15) return fail(SDM_ERR_INVALID, "too many refinement levels (max 15)");
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
-    k_refine<<<h->g_refine, 256, smem_for(h), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
-                                                           next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz);
+    k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
+                                                                next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz, h->grid);
     mark(h, "k_refine");
     h->stats.kernel_launches++;
     h->cur ^= 1; h->level++;
@@ -343,7 +390,7 @@ int enqueue_weld_clears(SdmHandle* h) {
 int enqueue_mesh_local(SdmHandle* h) {
     const float sx = h->voxel_size[0], sy = h->voxel_size[1], sz = h->voxel_size[2];
     const float* vox = h->vox[h->cur].p;
-    const size_t smem = smem_for(h);
+    const size_t smem = smem_for(h, 256), smem128 = smem_for(h, 128);
     cudaStream_t s = h->stream;
     const uint32_t mask = h->table_entries - 1;
     // the mesh stage may be re-run on the same field: reset the mesh-stage counters and tickets only
@@ -356,17 +403,17 @@ int enqueue_mesh_local(SdmHandle* h) {
     if (rc) return rc;
     mark(h, "clears");
     k_classify<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cases.p, h->tri_off.p,
-                                                 h->cap_tris, sx, sy, sz);
+                                                 h->cap_tris, sx, sy, sz, h->grid);
     mark(h, "k_classify");
     k_edges<<<h->g_light, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, mask, h->ustart.p, h->cap_uniq,
                                         h->slot_ref.p, sx, sy, sz);
     mark(h, "k_edges");
-    k_project<<<h->g_project, 128, smem, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq);
+    k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->grid);
     mark(h, "k_project");
-    k_vertex_normals<<<h->g_normals, 128, smem, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq);
+    k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid);
     mark(h, "k_vertex_normals");
-    k_orient<<<h->g_orient, 128, smem, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
-                                             h->tri_valid_bits.p);
+    k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
+                                                h->tri_valid_bits.p, h->grid);
     mark(h, "k_orient");
     h->stats.kernel_launches += 5;
     CK(cudaGetLastError());
@@ -472,6 +519,10 @@ int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count) {
     CK(cudaMemcpyAsync(h->scene.p, blob.data(), blob.size() * 16, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->scene_bytes = (uint32_t) (blob.size() * 16);
+    h->scene_nprims = reinterpret_cast<const SceneHeader*>(blob.data())->nprims;
+    // culling pays off once the table is long; it needs 1-Lipschitz primitives (not the Mandelbulb estimator)
+    h->mask_capable = !mb && h->scene_nprims > 24;
+    h->grid.enabled = 0;   // masks depend on the scene: rebuilt on the next remesh
     h->mesh_valid = false;
     return configure_kernels(h);
 }
@@ -520,6 +571,7 @@ void sdm_destroy(SdmHandle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->masks_fine.release(); h->masks_coarse.release();
     h->scene.release(); h->vox[0].release(); h->vox[1].release(); h->cases.release(); h->tri_off.release(); h->slot_ref.release();
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->out_idx.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
@@ -546,9 +598,13 @@ static int eval_common(SdmHandle* h, const float* points, uint32_t n, float* out
     if (iters) CK(cudaMalloc(&d_it, (size_t) n * 4));
     CK(cudaMemcpyAsync(d_in, points, (size_t) n * 12, cudaMemcpyHostToDevice, h->stream));
     const int grid = std::min<uint32_t>((n + 127) / 128, (uint32_t) h->num_sms * 8);
-    if (which == 0) k_eval_sdf<<<grid, 128, smem_for(h), h->stream>>>(h->scene.p, d_in, n, d_out);
-    else if (which == 1) k_eval_normal<<<grid, 128, smem_for(h), h->stream>>>(h->scene.p, d_in, n, d_out);
-    else k_eval_project<<<grid, 128, smem_for(h), h->stream>>>(h->scene.p, d_in, n, d_out, d_it);
+    if (h->mask_capable && !h->grid.enabled) {   // probes outside a remesh: default domain (bindings.h:9-10)
+        int rc = ensure_masks(h, SDM_MESH_GENERATION_BB_SIZE, 64);
+        if (rc) return rc;
+    }
+    if (which == 0) k_eval_sdf<<<grid, 128, smem_for(h, 128), h->stream>>>(h->scene.p, d_in, n, d_out, h->grid);
+    else if (which == 1) k_eval_normal<<<grid, 128, smem_for(h, 128), h->stream>>>(h->scene.p, d_in, n, d_out, h->grid);
+    else k_eval_project<<<grid, 128, smem_for(h, 128), h->stream>>>(h->scene.p, d_in, n, d_out, d_it, h->grid);
     h->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, (size_t) n * 4 * width, cudaMemcpyDeviceToHost, h->stream));
@@ -601,6 +657,10 @@ int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field) {
     if (rc) return rc;
     rc = reset_state(h);
     if (rc) return rc;
+    if (h->mask_capable && !h->grid.enabled) {   // an uploaded list carries no domain: masks over the default cube; points outside
+        rc = ensure_masks(h, SDM_MESH_GENERATION_BB_SIZE, 64);   // it simply use the full primitive list
+        if (rc) return rc;
+    }
     if (field->voxel_count)
         CK(cudaMemcpyAsync(h->vox[0].p, field->voxels, (size_t) field->voxel_count * 12, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(&h->state.p->level_count[0], &field->voxel_count, 4, cudaMemcpyHostToDevice, h->stream));
@@ -979,6 +1039,26 @@ int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangl
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->stats.last_gpu_ms = ms;
     mesh_view(h, out_mesh);
+    return SDM_OK;
+}
+
+// Debug / test access to intermediate device buffers of the last mesh stage (copies `bytes` bytes to host).
+int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes) {
+    if (!h || !name || !dst) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const std::string n(name);
+    const void* src = nullptr;
+    size_t have = 0;
+    if (n == "ustart") { src = h->ustart.p; have = h->ustart.n * 4; }
+    else if (n == "upos") { src = h->upos.p; have = h->upos.n * 4; }
+    else if (n == "unrm") { src = h->unrm.p; have = h->unrm.n * 4; }
+    else if (n == "tri_uid") { src = h->tri_uid.p; have = h->tri_uid.n * 4; }
+    else if (n == "tri_off") { src = h->tri_off.p; have = h->tri_off.n * 4; }
+    else if (n == "first_slot") { src = h->first_slot.p; have = h->first_slot.n * 4; }
+    else return fail(SDM_ERR_INVALID, "unknown buffer name");
+    if (bytes > have) return fail(SDM_ERR_INVALID, "buffer smaller than requested");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return SDM_OK;
 }
 

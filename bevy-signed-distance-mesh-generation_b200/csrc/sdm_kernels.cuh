@@ -101,9 +101,9 @@ __device__ __forceinline__ constexpr uint32_t child_mask(int i, int j, int k) {
 // inside-bits are gathered with one ballot; lane q then owns parent q's 27-bit mask.
 __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox,
                                                 float* __restrict__ out_vox, DevState* st, int level, uint32_t epoch,
-                                                uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz) {
+                                                uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz, MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
             by = in_vox[3 * (size_t) (p0 + lane) + 1];
             bz = in_vox[3 * (size_t) (p0 + lane) + 2];
         }
+        // primitives that can matter anywhere inside this tile's parent voxels (edge = 2 * child size)
+        tile_mask_from_box(grid, sc, lane < np, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
         uint32_t myword = 0;
         const uint32_t rounds = (27u * np + 31u) >> 5;
         for (uint32_t t = 0; t < rounds; t++) {
@@ -185,11 +187,11 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
 // One warp = 32 voxels = 256 corner samples = 8 ballots; voxel q's case byte is byte (q&3) of ballot (q>>2).
 __global__ void __launch_bounds__(256) k_classify(const uint4* __restrict__ scene, const float* __restrict__ vox, DevState* st,
                                                   int level, uint32_t epoch, uint64_t* tiles, uint8_t* __restrict__ cases,
-                                                  uint32_t* __restrict__ tri_off, uint32_t cap_tris, float sx, float sy, float sz) {
+                                                  uint32_t* __restrict__ tri_off, uint32_t cap_tris, float sx, float sy, float sz, MaskGrid grid) {
     extern __shared__ uint4 smem[];
     __shared__ unsigned char s_ntri[256];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = c_mc_ntri[i];
-    const SceneView sc = stage_scene(scene, smem);
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(256) k_classify(const uint4* __restrict__ scen
             by = vox[3 * (size_t) (p0 + lane) + 1];
             bz = vox[3 * (size_t) (p0 + lane) + 2];
         }
+        tile_mask_from_box(grid, sc, lane < np, bx, by, bz, bx + sx, by + sy, bz + sz);
         uint32_t myword = 0;
 #pragma unroll 1
         for (uint32_t t = 0; t < 8; t++) {
@@ -314,14 +317,16 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
 // closest_surface_point per distinct mid-point.  Lanes that finish pull the next vertex (warp-level refill from a
 // global ticket), so a warp's lanes stay busy although iteration counts differ per vertex.
 __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart,
-                                                 float* __restrict__ upos, uint32_t cap_uniq) {
+                                                 float* __restrict__ upos, uint32_t cap_uniq, MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(st->n_uniq, cap_uniq);
     bool have = false;
     uint32_t uid = 0, it = 0, iters_done = 0;
     float gx = 0.f, gy = 0.f, gz = 0.f;
+    NewtonCycle cyc;
+    cyc.start(0.f, 0.f, 0.f);
     bool drained = false;
     while (true) {
         const uint32_t need = __ballot_sync(0xffffffffu, !have);
@@ -334,15 +339,18 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
                 if (idx < n) {
                     uid = idx; it = 0; have = true;
                     gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
+                    cyc.start(gx, gy, gz);
                 }
             }
             if (base + __popc(need) >= n) drained = true;
         }
         if (!__any_sync(0xffffffffu, have)) break;
+        tile_mask_from_point(grid, sc, have, gx, gy, gz);   // cells of the lanes' current iterates
         if (have) {
             const bool collision = newton_step(sc, gx, gy, gz);
             it++;
-            if (collision || it >= 10000u) {   // for (i = 0; !collision && i < 10000; i++)
+            if (!collision) cyc.observe(gx, gy, gz, it);
+            if (collision || it >= cyc.stop_at) {   // for (i = 0; !collision && i < 10000; i++)
                 upos[3 * (size_t) uid] = gx; upos[3 * (size_t) uid + 1] = gy; upos[3 * (size_t) uid + 2] = gz;
                 iters_done += it;
                 have = false;
@@ -355,14 +363,24 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
 }
 
 __global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
-                                                        float* __restrict__ unrm, uint32_t cap_uniq) {
+                                                        float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t n = min(st->n_uniq, cap_uniq);
-    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
-        float nx, ny, nz;
-        empirical_normal(sc, upos[3 * (size_t) u], upos[3 * (size_t) u + 1], upos[3 * (size_t) u + 2], nx, ny, nz);
-        unrm[3 * (size_t) u] = nx; unrm[3 * (size_t) u + 1] = ny; unrm[3 * (size_t) u + 2] = nz;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t u0 = warp_id << 5; u0 < n; u0 += warps_total << 5) {   // warp-uniform trip count (tile masks are warp collectives)
+        const uint32_t u = u0 + lane;
+        const bool active = u < n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
+        tile_mask_from_point(grid, sc, active, x, y, z);
+        if (active) {
+            float nx, ny, nz;
+            empirical_normal(sc, x, y, z, nx, ny, nz);
+            unrm[3 * (size_t) u] = nx; unrm[3 * (size_t) u + 1] = ny; unrm[3 * (size_t) u + 2] = nz;
+        }
     }
 }
 
@@ -370,9 +388,9 @@ __global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict_
 __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene, DevState* st, const uint4* __restrict__ table,
                                                 const uint32_t* __restrict__ slot_ref, const float* __restrict__ upos,
                                                 uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
-                                                uint32_t* __restrict__ tri_valid_bits) {
+                                                uint32_t* __restrict__ tri_valid_bits, MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t T = st->n_tris_raw;
     if (st->error_flags) return;
     const uint32_t lane = threadIdx.x & 31u;
@@ -382,25 +400,28 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
     for (uint32_t t0 = warp_id << 5; t0 < T; t0 += warps_total << 5) {
         const uint32_t t = t0 + lane;
         bool valid = false;
+        uint32_t u[3] = { 0, 0, 0 };
+        float v[3][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
+        float mx = 0.f, my = 0.f, mz = 0.f;
         if (t < T) {
-            uint32_t u[3];
-            float v[3][3];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 u[j] = reinterpret_cast<const uint32_t*>(table + slot_ref[3 * (size_t) t + j])[3];
                 v[j][0] = upos[3 * (size_t) u[j]]; v[j][1] = upos[3 * (size_t) u[j] + 1]; v[j][2] = upos[3 * (size_t) u[j] + 2];
             }
-            // normalize(cross(v1 - v0, v2 - v0))   (compute_mesh_generation.cu:103)
+            // (v0 + v1 + v2) / 3.0f   (compute_mesh_generation.cu:104)
+            mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f; my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f; mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
+        }
+        tile_mask_from_point(grid, sc, t < T, mx, my, mz);
+        if (t < T) {
+            // normalize(cross(v1 - v0, v2 - v0))   (:103)
             const float ax = v[1][0] - v[0][0], ay = v[1][1] - v[0][1], az = v[1][2] - v[0][2];
             const float bx = v[2][0] - v[0][0], by = v[2][1] - v[0][1], bz = v[2][2] - v[0][2];
             const float cx = ay * bz - by * az, cy = az * bx - bz * ax, cz = ax * by - bx * ay;
             const float inv = 1.0f / sqrtf(dot3(cx, cy, cz, cx, cy, cz));
             const float tnx = cx * inv, tny = cy * inv, tnz = cz * inv;
-            // empirical_normal(sd_obj, (v0 + v1 + v2) / 3.0f)   (:104)
-            const float mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f, my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f,
-                        mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
             float nx, ny, nz;
-            empirical_normal(sc, mx, my, mz, nx, ny, nz);
+            empirical_normal(sc, mx, my, mz, nx, ny, nz);   // empirical_normal(sd_obj, centroid)   (:104)
             const bool flip = dot3(tnx, tny, tnz, nx, ny, nz) <= 0.0f;   // :105
             const uint32_t f0 = flip ? u[2] : u[0], f2 = flip ? u[0] : u[2];
             const float first_x = flip ? v[2][0] : v[0][0];
@@ -607,32 +628,129 @@ __global__ void __launch_bounds__(256) k_first_slot_merged(DevState* st, uint32_
 }
 
 // ---- test / probe kernels -------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_eval_sdf(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_eval_sdf(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out,
+                                                  MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        out[i] = eval_scene1(sc, pts[3 * (size_t) i], pts[3 * (size_t) i + 1], pts[3 * (size_t) i + 2]);
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t i0 = warp_id << 5; i0 < n; i0 += warps_total << 5) {
+        const uint32_t i = i0 + lane;
+        const bool active = i < n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) { x = pts[3 * (size_t) i]; y = pts[3 * (size_t) i + 1]; z = pts[3 * (size_t) i + 2]; }
+        tile_mask_from_point(grid, sc, active, x, y, z);
+        if (active) out[i] = eval_scene1(sc, x, y, z);
+    }
 }
-__global__ void __launch_bounds__(128) k_eval_normal(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_eval_normal(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out,
+                                                     MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float nx, ny, nz;
-        empirical_normal(sc, pts[3 * (size_t) i], pts[3 * (size_t) i + 1], pts[3 * (size_t) i + 2], nx, ny, nz);
-        out[3 * (size_t) i] = nx; out[3 * (size_t) i + 1] = ny; out[3 * (size_t) i + 2] = nz;
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t i0 = warp_id << 5; i0 < n; i0 += warps_total << 5) {
+        const uint32_t i = i0 + lane;
+        const bool active = i < n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) { x = pts[3 * (size_t) i]; y = pts[3 * (size_t) i + 1]; z = pts[3 * (size_t) i + 2]; }
+        tile_mask_from_point(grid, sc, active, x, y, z);
+        if (active) {
+            float nx, ny, nz;
+            empirical_normal(sc, x, y, z, nx, ny, nz);
+            out[3 * (size_t) i] = nx; out[3 * (size_t) i + 1] = ny; out[3 * (size_t) i + 2] = nz;
+        }
     }
 }
 __global__ void __launch_bounds__(128) k_eval_project(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n,
-                                                      float* __restrict__ out, uint32_t* __restrict__ iters) {
+                                                      float* __restrict__ out, uint32_t* __restrict__ iters, MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float gx = pts[3 * (size_t) i], gy = pts[3 * (size_t) i + 1], gz = pts[3 * (size_t) i + 2];
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t i0 = warp_id << 5; i0 < n; i0 += warps_total << 5) {
+        const uint32_t i = i0 + lane;
+        bool running = i < n;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (running) { gx = pts[3 * (size_t) i]; gy = pts[3 * (size_t) i + 1]; gz = pts[3 * (size_t) i + 2]; }
         uint32_t it = 0;
         bool collision = false;
-        while (!collision && it < 10000u) { collision = newton_step(sc, gx, gy, gz); it++; }
-        out[3 * (size_t) i] = gx; out[3 * (size_t) i + 1] = gy; out[3 * (size_t) i + 2] = gz;
-        if (iters) iters[i] = it;
+        NewtonCycle cyc;
+        cyc.start(gx, gy, gz);
+        while (__any_sync(0xffffffffu, running)) {
+            tile_mask_from_point(grid, sc, running, gx, gy, gz);
+            if (running) {
+                collision = newton_step(sc, gx, gy, gz);
+                it++;
+                if (!collision) cyc.observe(gx, gy, gz, it);
+                running = !collision && it < cyc.stop_at;
+            }
+        }
+        if (i < n) {
+            out[3 * (size_t) i] = gx; out[3 * (size_t) i + 1] = gy; out[3 * (size_t) i + 2] = gz;
+            if (iters) iters[i] = collision ? it : 10000u;   // the reference's iteration count
+        }
+    }
+}
+
+// ---- primitive masks --------------------------------------------------------------------------------------
+// For a cell with centre c and radius rho (circumsphere of the cell cube + slop, see host code), primitive i is dropped
+// iff   d_i(c) - rho  >=  U_i + k_i + margin,   U_i = min over earlier primitives j < i (of the parent cell's mask, or
+// all of them) of d_j(c) + rho.
+// Why that is exact.  All primitive kinds admitted here (sphere, capsule, box) are 1-Lipschitz distance functions, so for
+// every p within rho of c:  d_i(p) >= d_i(c) - rho  and  d_j(p) <= d_j(c) + rho.  The fold accumulator never exceeds the
+// minimum of the distances folded so far (fminf(a,b) - h*h*h*k/6 <= fminf(a,b); signed_distance.cu:21-22), and a
+// skipped primitive leaves it unchanged, so acc_i(p) <= U_i.  Hence d_i(p) - acc_i(p) >= k_i + margin: for smooth_min,
+// k - |acc - d| <= 0 gives h = 0 and the result is fminf(acc, d) - 0 = acc bit for bit; for min, fminf(acc, d) = acc.
+// The margin (1e-4) is orders of magnitude above the rounding error of the distances involved (|d| < ~10).
+// With parent masks (coarse grid, 4x4x4 fine cells per coarse cell) only primitives of the parent's mask are tested:
+// a primitive outside the parent's mask is already proven droppable on the parent's sphere, which contains the child's.
+__global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ scene, uint32_t* __restrict__ out_masks, MaskGrid g,
+                                                     const uint32_t* __restrict__ parent_masks, uint32_t parent_G, float rho) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene(scene, smem);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t ncells = g.G * g.G * g.G;
+    const float inf = __int_as_float(0x7f800000);
+    for (uint32_t cell = warp_id; cell < ncells; cell += warps_total) {
+        const uint32_t iz = cell % g.G, iy = (cell / g.G) % g.G, ix = cell / (g.G * g.G);
+        const float cx = g.ox + ((float) ix + 0.5f) * g.cell, cy = g.oy + ((float) iy + 0.5f) * g.cell, cz = g.oz + ((float) iz + 0.5f) * g.cell;
+        const uint32_t* prow = nullptr;
+        if (parent_masks) {
+            const uint32_t f = g.G / parent_G;
+            prow = parent_masks + ((size_t) (((ix / f) * parent_G + iy / f) * parent_G + iz / f)) * g.W;
+        }
+        float carry = inf;
+        for (uint32_t w = 0; w < g.W; w++) {
+            const uint32_t pm = prow ? prow[w] : 0xFFFFFFFFu;
+            uint32_t word = 0;
+            if (pm) {
+                const uint32_t j = (w << 5) + lane;
+                const bool active = ((pm >> lane) & 1u) && j < sc.nprims;
+                float d = inf, kk = 0.0f;
+                if (active) {
+                    const DevPrim c = sc.prims[j];
+                    d = prim_distance(c, cx, cy, cz);
+                    kk = c.fold == SDM_FOLD_SMOOTH_MIN ? c.k : 0.0f;
+                }
+                const float ub = d + rho;
+                float e = ub;   // inclusive prefix-min over lanes, then shifted to exclusive
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v = __shfl_up_sync(0xffffffffu, e, o);
+                    if (lane >= (uint32_t) o) e = fminf(e, v);
+                }
+                const float total = __shfl_sync(0xffffffffu, e, 31);
+                float excl = __shfl_up_sync(0xffffffffu, e, 1);
+                if (lane == 0) excl = inf;
+                const float U = fminf(carry, excl);
+                const bool keep = active && !(d - rho >= U + kk + 1e-4f);   // NaN distance: keep
+                word = __ballot_sync(0xffffffffu, keep);
+                carry = fminf(carry, total);
+            }
+            if (lane == 0) out_masks[(size_t) cell * g.W + w] = word;
+        }
     }
 }
 

@@ -204,6 +204,9 @@ int sdm_get_stats(SdmHandle* h, SdmStats* out);
 /* Per-kernel timing for the bench's roofline line: when enabled, sdm_remesh records a CUDA event on the handle's
  * stream after every kernel it enqueues; sdm_get_kernel_times returns (name, ms) per kernel of the last remesh. */
 int sdm_set_profiling(SdmHandle* h, int enabled);
+/* Test access to intermediate device buffers of the last mesh stage ("ustart", "upos", "unrm", "tri_uid", "tri_off",
+ * "first_slot"): copies `bytes` bytes to host memory. */
+int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes);
 int sdm_get_kernel_times(SdmHandle* h, const char** names, float* ms, uint32_t capacity);
 
 #ifdef __cplusplus
