@@ -189,7 +189,10 @@ struct SdmHandle {
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix, out_idx;
     DevBuf<float> ustart, upos, unrm, out_pos, out_nrm;
     DevBuf<uint4> table1, table2;
-    DevBuf<uint64_t> tiles;
+    DevBuf<uint64_t> tiles, tiles2;
+    DevBuf<Straggler> stragglers;
+    uint32_t cap_stragglers = 0;
+    uint32_t table1_entries = 0;        // entries of table1 actually used (adaptive: sized from the previous mesh)
     DevBuf<DevState> state;
     DevState* host_state = nullptr;   // pinned
     DevBuf<uint32_t> shard_range;     // {lo, hi, n} of the last k_take_shard
@@ -199,7 +202,7 @@ struct SdmHandle {
     bool mesh_valid = false;
 
     // persistent grid sizes
-    int g_refine = 0, g_classify = 0, g_project = 0, g_normals = 0, g_orient = 0, g_light = 0;
+    int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0;
 
     SdmStats stats {};
 
@@ -250,9 +253,9 @@ int configure_kernels(SdmHandle* h) {
     if (smem_for(h, 256) > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
     struct K { const void* f; int threads; int* grid; };
     const K ks[] = {
-        { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify, 256, &h->g_classify },
+        { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify_edges, 256, &h->g_classify },
         { (const void*) k_project, 128, &h->g_project }, { (const void*) k_vertex_normals, 128, &h->g_normals },
-        { (const void*) k_orient, 128, &h->g_orient },
+        { (const void*) k_orient, 128, &h->g_orient },   { (const void*) k_project_tail, 128, &h->g_tail },
     };
     for (const K& k : ks) {
         const size_t smem = smem_for(h, k.threads);
@@ -331,6 +334,12 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     const size_t old_tiles = h->tiles.n;
     CK(h->tiles.reserve(max_tiles));
     if (h->tiles.n != old_tiles) CK(cudaMemsetAsync(h->tiles.p, 0, h->tiles.n * sizeof(uint64_t), h->stream));
+    const size_t old_tiles2 = h->tiles2.n;
+    CK(h->tiles2.reserve((size_t) cap_vox / 32 + 64));
+    if (h->tiles2.n != old_tiles2) CK(cudaMemsetAsync(h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t), h->stream));
+    h->cap_stragglers = h->cap_uniq / 8 + 4096;
+    CK(h->stragglers.reserve(h->cap_stragglers));
+    h->table1_entries = h->table_entries;
     h->have_field = false;
     h->mesh_valid = false;
     return SDM_OK;
@@ -340,6 +349,7 @@ uint32_t next_epoch(SdmHandle* h) {
     h->epoch++;
     if (h->epoch >= (1u << 30)) {   // wrap: make every stale descriptor invalid again
         cudaMemsetAsync(h->tiles.p, 0, h->tiles.n * sizeof(uint64_t), h->stream);
+        cudaMemsetAsync(h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t), h->stream);
         h->epoch = 1;
     }
     return h->epoch;
@@ -377,39 +387,40 @@ int enqueue_refine(SdmHandle* h) {
     return SDM_OK;
 }
 
-int enqueue_weld_clears(SdmHandle* h) {
-    cudaStream_t s = h->stream;
-    CK(cudaMemsetAsync(&h->state.p->n_tris_out, 0, 8, s));   // n_tris_out, n_verts_out
-    CK(cudaMemsetAsync(&h->state.p->ticket[TK_SCAN_FIRST], 0, 8, s));
-    CK(cudaMemsetAsync(h->table2.p, 0xFF, (size_t) h->table_entries * 16, s));
-    CK(cudaMemsetAsync(h->first_bits.p, 0, h->first_bits.n * 4, s));
+// clears sized on the device from n_uniq / n_tris_raw (which must already be in DevState)
+int enqueue_weld_clears(SdmHandle* h, bool clear_first_slot) {
+    k_clear_weld_state<<<h->g_light, 256, 0, h->stream>>>(h->state.p, h->first_slot.p, h->first_bits.p, h->table2.p, h->table_entries,
+                                                          h->cap_uniq, clear_first_slot ? 1 : 0);
+    h->stats.kernel_launches++;
     return SDM_OK;
 }
 
-// classify -> edges -> project -> normals -> orient: everything that needs only this handle's voxels
+// classify+edges -> project (+tail) -> normals -> orient: everything that needs only this handle's voxels
 int enqueue_mesh_local(SdmHandle* h) {
     const float sx = h->voxel_size[0], sy = h->voxel_size[1], sz = h->voxel_size[2];
     const float* vox = h->vox[h->cur].p;
     const size_t smem = smem_for(h, 256), smem128 = smem_for(h, 128);
     cudaStream_t s = h->stream;
-    const uint32_t mask = h->table_entries - 1;
-    // the mesh stage may be re-run on the same field: reset the mesh-stage counters and tickets only
-    CK(cudaMemsetAsync(&h->state.p->n_tris_raw, 0, offsetof(DevState, error_flags) - offsetof(DevState, n_tris_raw), s));   // not error_flags
-    CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY), s));
+    // the mesh stage may be re-run on the same field: reset the mesh-stage counters and tickets only (not error_flags)
+    CK(cudaMemsetAsync(&h->state.p->n_tris_raw, 0, offsetof(DevState, error_flags) - offsetof(DevState, n_tris_raw), s));
+    CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY + 1), s));   // + n_stragglers
     CK(cudaMemsetAsync(&h->state.p->newton_iters, 0, sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table_entries * 16, s));
-    CK(cudaMemsetAsync(h->first_slot.p, 0xFF, (size_t) h->cap_uniq * 4, s));
-    int rc = enqueue_weld_clears(h);
-    if (rc) return rc;
+    // vertex de-duplication table: sized from the previous mesh of this handle (4x its vertex count), full size at first;
+    // an overflow is detected (ERR_HASH_FULL) and retried with the full table
+    CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table1_entries * 16, s));
     mark(h, "clears");
-    k_classify<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cases.p, h->tri_off.p,
-                                                 h->cap_tris, sx, sy, sz, h->grid);
-    mark(h, "k_classify");
-    k_edges<<<h->g_light, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, mask, h->ustart.p, h->cap_uniq,
-                                        h->slot_ref.p, sx, sy, sz);
-    mark(h, "k_edges");
-    k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->grid);
+    const uint32_t e_tri = next_epoch(h), e_uid = next_epoch(h);
+    k_classify_edges<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, e_tri, e_uid, h->tiles.p, h->tiles2.p, h->cases.p,
+                                                       h->tri_off.p, h->cap_tris, h->table1.p, h->table1_entries - 1, h->ustart.p, h->cap_uniq,
+                                                       h->slot_ref.p, sx, sy, sz, h->grid);
+    mark(h, "k_classify_edges");
+    int rc = enqueue_weld_clears(h, true);
+    if (rc) return rc;
+    mark(h, "k_clear_weld_state");
+    k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid);
     mark(h, "k_project");
+    k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid);
+    mark(h, "k_project_tail");
     k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid);
     mark(h, "k_vertex_normals");
     k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
@@ -423,8 +434,7 @@ int enqueue_mesh_local(SdmHandle* h) {
 // the reference-order weld over (upos, unrm, tri_uid, first_slot, tri_valid_bits) and the counters in DevState
 int enqueue_weld(SdmHandle* h) {
     cudaStream_t s = h->stream;
-    const uint32_t mask = h->table_entries - 1;
-    k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, mask, h->wref.p, h->cap_uniq);
+    k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, h->table_entries, h->wref.p, h->cap_uniq);
     mark(h, "k_weld_insert");
     k_weld_mark<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->cap_uniq);
     mark(h, "k_weld_mark");
@@ -488,6 +498,17 @@ int check_params(const SdmParams& p) {
 }
 
 uint32_t grown(uint32_t cap) { return (uint32_t) std::min<uint64_t>((uint64_t) cap * 2, 1ull << 30); }
+
+// after a successful mesh: size the vertex table of the next mesh from this one
+void adapt_table1(SdmHandle* h) {
+    const uint32_t want = pow2_at_least(std::max<uint64_t>((uint64_t) h->host_state->n_uniq * 4, 1u << 16));
+    h->table1_entries = std::min(want, h->table_entries);
+}
+// the adaptive vertex table was too small (and nothing else overflowed): retry with the full table, same capacities
+bool only_table1_overflow(SdmHandle* h, uint32_t flags) {
+    if (flags == ERR_HASH_FULL && h->table1_entries < h->table_entries) { h->table1_entries = h->table_entries; return true; }
+    return false;
+}
 
 }  // namespace
 
@@ -575,7 +596,7 @@ void sdm_destroy(SdmHandle* h) {
     h->scene.release(); h->vox[0].release(); h->vox[1].release(); h->cases.release(); h->tri_off.release(); h->slot_ref.release();
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->out_idx.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
-    h->out_pos.release(); h->out_nrm.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->state.release();
+    h->out_pos.release(); h->out_nrm.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     h->shard_range.release();
@@ -753,8 +774,13 @@ static int run_mesh(SdmHandle* h, SdmMesh* out_mesh, bool timed) {
             if (timed) { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.last_gpu_ms = ms; }
             h->mesh_valid = true;
             fill_stats(h, true);
+            adapt_table1(h);
             if (out_mesh) mesh_view(h, out_mesh);
             return SDM_OK;
+        }
+        if (only_table1_overflow(h, flags)) {
+            CK(cudaMemsetAsync(&h->state.p->error_flags, 0, 4, h->stream));
+            continue;
         }
         // a mesh-stage capacity was exceeded: keep the field (download / grow / upload) and retry
         const uint32_t n = h->host_state->level_count[h->level];
@@ -841,9 +867,11 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
             h->mesh_valid = true;
             fill_stats(h, true);
             prof_end(h);
+            adapt_table1(h);
             mesh_view(h, out_mesh);
             return SDM_OK;
         }
+        if (only_table1_overflow(h, flags)) continue;
         want = grown(h->cap_vox);
         if (want == h->cap_vox) break;
     }
@@ -957,12 +985,14 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
             prof_end(h);
             h->own_tris = h->host_state->n_tris_raw;
             h->own_uniq = h->host_state->n_uniq;
+            adapt_table1(h);
             out_info->shard_index = shard_index; out_info->shard_count = shard_count; out_info->split_level = split_level;
             out_info->voxel_begin = h->host_range[0]; out_info->voxel_end = h->host_range[1]; out_info->split_total = h->host_range[2];
             out_info->final_voxels = h->host_state->level_count[h->level];
             out_info->unique_vertices = h->own_uniq; out_info->raw_triangles = h->own_tris;
             return SDM_OK;
         }
+        if (only_table1_overflow(h, flags)) continue;
         want = grown(h->cap_vox);
         if (want == h->cap_vox) break;
     }
@@ -1023,9 +1053,8 @@ int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangl
     uint32_t* counts = h->host_range;   // pinned scratch: {n_tris_raw, n_uniq}
     counts[0] = total_triangles; counts[1] = total_vertices;
     CK(cudaMemcpyAsync(&h->state.p->n_tris_raw, counts, 8, cudaMemcpyHostToDevice, s));   // n_tris_raw, n_uniq are adjacent
-    int rc = enqueue_weld_clears(h);
+    int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->first_slot.p, 0xFF, (size_t) total_vertices * 4, s));
     k_first_slot_merged<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->first_slot.p, h->tri_valid_bits.p, h->own_tris);
     h->stats.kernel_launches++;
     rc = enqueue_weld(h);

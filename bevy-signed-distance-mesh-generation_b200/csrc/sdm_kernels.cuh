@@ -3,10 +3,10 @@
 //   k_init_field      level-0 dense list                       (src/cuda/mod.rs:105-122)
 //   k_refine          3x3x3 lattice classification + stable compaction of surviving children
 //                     (compute_mesh_generation.cu:12-62 + src/cuda/mod.rs:179-194)
-//   k_classify        8 corner signs -> case index, triangle count, triangle offsets
-//                     (compute_mesh_generation.cu:77-86, marching_cubes.cu:19-25)
-//   k_edges           edge mid-points (marching_cubes.cu:13-16) de-duplicated by exact bit pattern
-//   k_project         closest_surface_point per distinct mid-point (signed_distance.cu:227-240)
+//   k_classify_edges  8 corner signs -> case index, triangle count/offsets (compute_mesh_generation.cu:77-86,
+//                     marching_cubes.cu:19-25); edge mid-points (marching_cubes.cu:13-16) de-duplicated by exact bit pattern
+//   k_project(+_tail) closest_surface_point per distinct mid-point (signed_distance.cu:227-240)
+//   k_build_masks     per-cell primitive masks for large scenes (exact culling of the fold)
 //   k_vertex_normals  empirical_normal per projected vertex (signed_distance.cu:181-202)
 //   k_orient          per triangle: face normal vs. centroid normal, flip (compute_mesh_generation.cu:103-113),
 //                     finite filter (src/cuda/mod.rs:289), first-occurrence slot per vertex
@@ -26,7 +26,7 @@ namespace sdm {
 
 namespace cg = cooperative_groups;
 
-enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_COUNT = 24 };
+enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_COUNT = 24 };
 enum ErrFlag : uint32_t {
     ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u
 };
@@ -39,7 +39,7 @@ struct DevState {
     uint32_t n_verts_out;       // welded vertices
     uint32_t error_flags;
     uint32_t ticket[TK_COUNT];
-    uint32_t pad;
+    uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
 };
 
@@ -97,8 +97,21 @@ __device__ __forceinline__ constexpr uint32_t child_mask(int i, int j, int k) {
     return m;
 }
 
-// One warp = one tile of 32 parents.  864 lattice points are spread over the 32 lanes (27 rounds), each round's
-// inside-bits are gathered with one ballot; lane q then owns parent q's 27-bit mask.
+__device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t) o) v += t;
+    }
+    return v;
+}
+
+// One warp = one tile of 32 parents, one lane = one parent.  The reference tests the 8 corners of each of the 8 children
+// (<= 64 evaluations, compute_mesh_generation.cu:30-49); the corners are the 27 points of the parent's 3x3x3 lattice
+// (`upper` of child i is `lower` of child i+1: the same float expression base + vec3{i,j,k} * size), so 27 evaluations
+// give the same 64 signs.  They are done as three x-slabs of 9 points held in registers (ILP 9 per lane).
+// Surviving children are appended in the reference's order (n_id = id*8 + i*4 + j*2 + k, :51; Vec::retain is stable,
+// src/cuda/mod.rs:192) at the offset given by a warp scan + decoupled look-back across tiles.
 __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox,
                                                 float* __restrict__ out_vox, DevState* st, int level, uint32_t epoch,
                                                 uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz, MaskGrid grid) {
@@ -117,53 +130,43 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
         }
         const uint32_t p0 = tile << 5;
         const uint32_t np = min(32u, n - p0);
+        const bool active = lane < np;
         float bx = 0.f, by = 0.f, bz = 0.f;
-        if (lane < np) {
+        if (active) {
             bx = in_vox[3 * (size_t) (p0 + lane) + 0];
             by = in_vox[3 * (size_t) (p0 + lane) + 1];
             bz = in_vox[3 * (size_t) (p0 + lane) + 2];
         }
         // primitives that can matter anywhere inside this tile's parent voxels (edge = 2 * child size)
-        tile_mask_from_box(grid, sc, lane < np, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
-        uint32_t myword = 0;
-        const uint32_t rounds = (27u * np + 31u) >> 5;
-        for (uint32_t t = 0; t < rounds; t++) {
-            const uint32_t idx = (t << 5) + lane;
-            const uint32_t q = idx / 27u;
-            const uint32_t l = idx - q * 27u;
-            const float qx = __shfl_sync(0xffffffffu, bx, q & 31u);
-            const float qy = __shfl_sync(0xffffffffu, by, q & 31u);
-            const float qz = __shfl_sync(0xffffffffu, bz, q & 31u);
-            const uint32_t a = l / 9u, b = (l / 3u) % 3u, c = l % 3u;
-            // base + vec3{i,j,k} * output_voxel_size (compute_mesh_generation.cu:33-34); lattice step 2 is the
-            // `upper` of child 1 (i+1 = 2), step 1 is both `upper` of child 0 and `lower` of child 1.
-            const float x = qx + (float) a * osx, y = qy + (float) b * osy, z = qz + (float) c * osz;
-            bool inside = false;
-            if (q < np) inside = eval_scene1(sc, x, y, z) <= 0.0f;   // obj_contains, :8-10
-            const uint32_t w = __ballot_sync(0xffffffffu, inside);
-            if (lane == t) myword = w;
+        tile_mask_from_box(grid, sc, active, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
+        uint32_t m27 = 0;
+        if (active) {
+#pragma unroll 1
+            for (int a = 0; a < 3; a++) {
+                float px[9], py[9], pz[9], f[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) {
+                    // base + vec3{i,j,k} * output_voxel_size (compute_mesh_generation.cu:33-34)
+                    px[q] = bx + (float) a * osx;
+                    py[q] = by + (float) (q / 3) * osy;
+                    pz[q] = bz + (float) (q % 3) * osz;
+                }
+                eval_scene<9>(sc, px, py, pz, f);
+#pragma unroll
+                for (int q = 0; q < 9; q++) m27 |= (uint32_t) (f[q] <= 0.0f) << (a * 9 + q);   // obj_contains, :8-10
+            }
         }
-        const uint32_t bit0 = lane * 27u;
-        const uint32_t w0 = bit0 >> 5, sh = bit0 & 31u;
-        const uint32_t lo = __shfl_sync(0xffffffffu, myword, w0);
-        const uint32_t hi = __shfl_sync(0xffffffffu, myword, (w0 + 1u) & 31u);
-        const uint32_t m27 = (uint32_t) ((((uint64_t) hi << 32) | lo) >> sh) & 0x7FFFFFFu;
         uint32_t keep = 0;
-        if (lane < np) {
+        if (active) {
 #pragma unroll
             for (int ch = 0; ch < 8; ch++) {
                 const uint32_t M = child_mask(ch >> 2, (ch >> 1) & 1, ch & 1);
-                const uint32_t s = m27 & M;
-                keep |= (uint32_t) (s != 0u && s != M) << ch;   // is_border: corners do not all agree (:36-49)
+                const uint32_t sgn = m27 & M;
+                keep |= (uint32_t) (sgn != 0u && sgn != M) << ch;   // is_border: corners do not all agree (:36-49)
             }
         }
         const uint32_t cnt = __popc(keep);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t) o) incl += v;
-        }
+        const uint32_t incl = warp_inclusive_sum(cnt, lane);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
         uint32_t pos = excl_tile + incl - cnt;
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
             if (lane == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
         } else {
 #pragma unroll
-            for (int ch = 0; ch < 8; ch++) {   // child order n_id = id*8 + i*4 + j*2 + k (:51); stable
+            for (int ch = 0; ch < 8; ch++) {
                 if (keep & (1u << ch)) {
                     out_vox[3 * (size_t) pos + 0] = bx + (float) (ch >> 2) * osx;
                     out_vox[3 * (size_t) pos + 1] = by + (float) ((ch >> 1) & 1) * osy;
@@ -184,14 +187,28 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
     }
 }
 
-// One warp = 32 voxels = 256 corner samples = 8 ballots; voxel q's case byte is byte (q&3) of ballot (q>>2).
-__global__ void __launch_bounds__(256) k_classify(const uint4* __restrict__ scene, const float* __restrict__ vox, DevState* st,
-                                                  int level, uint32_t epoch, uint64_t* tiles, uint8_t* __restrict__ cases,
-                                                  uint32_t* __restrict__ tri_off, uint32_t cap_tris, float sx, float sy, float sz, MaskGrid grid) {
+// Marching-cubes classification and edge vertices of one tile of 32 voxels (one lane = one voxel):
+//   * 8 corner evaluations in registers -> cube_index (marching_cubes.cu:19-23), triangle count from the table
+//   * every edge the case uses gets its mid-point mix(a, b, 0.5f) (marching_cubes.cu:13-16), de-duplicated across
+//     voxels by the exact bit pattern of the mid-point in a 128-bit-CAS hash table: an identical start point gives an
+//     identical projection, normal and weld key, so it is projected once instead of once per incident triangle
+//     (~6x); mid-points that differ in any bit stay separate and are merged - if at all - by the reference's quantised
+//     weld later, exactly as the reference would
+//   * two look-backs give the tile's triangle offset and the ids of the vertices it created; ids are handed out in
+//     list order, so consecutive ids are spatial neighbours (this keeps the later per-vertex kernels' primitive
+//     masks small and their loads coalesced)
+//   * slot_ref[3*triangle + corner] = hash entry of that corner's vertex.
+__global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict__ scene, const float* __restrict__ vox, DevState* st,
+                                                        int level, uint32_t epoch_tri, uint32_t epoch_uid, uint64_t* tiles_tri, uint64_t* tiles_uid,
+                                                        uint8_t* __restrict__ cases, uint32_t* __restrict__ tri_off, uint32_t cap_tris,
+                                                        uint4* table, uint32_t table_mask, float* __restrict__ ustart, uint32_t cap_uniq,
+                                                        uint32_t* __restrict__ slot_ref, float sx, float sy, float sz, MaskGrid grid) {
     extern __shared__ uint4 smem[];
-    __shared__ unsigned char s_ntri[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = c_mc_ntri[i];
-    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    __shared__ McShared mc;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        mc.packed[i] = c_mc_packed[i]; mc.edgemask[i] = c_mc_edgemask[i]; mc.ntri[i] = c_mc_ntri[i];
+    }
+    const SceneView sc = stage_scene_masked(scene, smem, grid);   // ends with __syncthreads
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
@@ -200,75 +217,30 @@ __global__ void __launch_bounds__(256) k_classify(const uint4* __restrict__ scen
         if (lane == 0) tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) {
-            if (tile == 0 && lane == 0) st->n_tris_raw = 0;
+            if (tile == 0 && lane == 0) { st->n_tris_raw = 0; st->n_uniq = 0; }
             break;
         }
-        const uint32_t p0 = tile << 5;
-        const uint32_t np = min(32u, n - p0);
+        const uint32_t v = (tile << 5) + lane;
+        const bool active = v < n;
         float bx = 0.f, by = 0.f, bz = 0.f;
-        if (lane < np) {
-            bx = vox[3 * (size_t) (p0 + lane) + 0];
-            by = vox[3 * (size_t) (p0 + lane) + 1];
-            bz = vox[3 * (size_t) (p0 + lane) + 2];
-        }
-        tile_mask_from_box(grid, sc, lane < np, bx, by, bz, bx + sx, by + sy, bz + sz);
-        uint32_t myword = 0;
-#pragma unroll 1
-        for (uint32_t t = 0; t < 8; t++) {
-            const uint32_t idx = (t << 5) + lane;
-            const uint32_t q = idx >> 3;
-            const int c = (int) (idx & 7u);
-            const float qx = __shfl_sync(0xffffffffu, bx, q);
-            const float qy = __shfl_sync(0xffffffffu, by, q);
-            const float qz = __shfl_sync(0xffffffffu, bz, q);
-            float x, y, z;
-            voxel_corner(qx, qy, qz, sx, sy, sz, c, x, y, z);
-            bool inside = false;
-            if (q < np) inside = eval_scene1(sc, x, y, z) <= 0.0f;   // marching_cubes.cu:22
-            const uint32_t w = __ballot_sync(0xffffffffu, inside);
-            if (lane == t) myword = w;
-        }
-        const uint32_t w = __shfl_sync(0xffffffffu, myword, lane >> 2);
-        const uint32_t cube_index = (w >> ((lane & 3u) * 8u)) & 0xFFu;
-        const uint32_t cnt = lane < np ? s_ntri[cube_index] : 0u;
-        uint32_t incl = cnt;
+        if (active) { bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2]; }
+        tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
+        float cxs[8], cys[8], czs[8];
+        uint32_t cube_index = 0;
+        if (active) {
+            float f[8];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t) o) incl += v;
+            for (int c = 0; c < 8; c++) voxel_corner(bx, by, bz, sx, sy, sz, c, cxs[c], cys[c], czs[c]);   // :77-86
+            eval_scene<8>(sc, cxs, cys, czs, f);
+#pragma unroll
+            for (int c = 0; c < 8; c++) cube_index |= (uint32_t) (f[c] <= 0.0f) << c;   // marching_cubes.cu:22
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
-        if (lane < np) {
-            cases[p0 + lane] = (uint8_t) cube_index;
-            tri_off[p0 + lane] = excl_tile + incl - cnt;
-        }
-        if (tile == ntiles - 1 && lane == 0) {
-            const uint32_t T = excl_tile + total;
-            if (T > cap_tris) atomicOr(&st->error_flags, ERR_TRI_CAP);
-            st->n_tris_raw = min(T, cap_tris);
-        }
-    }
-}
-
-// Edge mid-points, de-duplicated by the exact bit pattern of the mid-point (identical start point => identical
-// projection, normal and weld key; mid-points that differ in any bit stay separate and are merged, if at all,
-// by the quantised weld exactly as in the reference).
-__global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
-                                               const uint32_t* __restrict__ tri_off, uint4* table, uint32_t table_mask,
-                                               float* __restrict__ ustart, uint32_t cap_uniq, uint32_t* __restrict__ slot_ref,
-                                               float sx, float sy, float sz) {
-    __shared__ McShared mc;
-    stage_mc(&mc);
-    const uint32_t n = st->level_count[level];
-    if (st->error_flags & ERR_TRI_CAP) return;
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
-        const uint32_t cube_index = cases[v];
-        const uint32_t ntri = mc.ntri[cube_index];
-        if (ntri == 0) continue;
-        const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
-        const uint32_t emask = mc.edgemask[cube_index];
+        const uint32_t ntri = active ? mc.ntri[cube_index] : 0u;
+        // --- edges: find-or-insert the mid-points; remember the table entry per edge and which ones this lane created
+        const uint32_t emask = active ? mc.edgemask[cube_index] : 0u;
         uint32_t eref[12];
+        uint32_t won_mask = 0;
+        bool full = false;
 #pragma unroll
         for (int e = 0; e < 12; e++) {
             eref[e] = 0xFFFFFFFFu;
@@ -276,52 +248,99 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
                 // MC_EDGE_TABLE (marching_cubes_constants.cu:3-16)
                 const int c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
                 const int c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
-                float ax, ay, az, cx, cy, cz;
-                voxel_corner(bx, by, bz, sx, sy, sz, c0, ax, ay, az);
-                voxel_corner(bx, by, bz, sx, sy, sz, c1, cx, cy, cz);
-                // mix(a, b, 0.5f) = a * (1.0f - 0.5f) + b * 0.5f   (marching_cubes.cu:13-16)
-                const float mx = ax * (1.0f - 0.5f) + cx * 0.5f, my = ay * (1.0f - 0.5f) + cy * 0.5f, mz = az * (1.0f - 0.5f) + cz * 0.5f;
-                uint32_t kx = __float_as_uint(mx), ky = __float_as_uint(my), kz = __float_as_uint(mz);
+                // mix(a, b, 0.5f) = a * (1.0f - 0.5f) + b * 0.5f
+                const float mx = cxs[c0] * (1.0f - 0.5f) + cxs[c1] * 0.5f, my = cys[c0] * (1.0f - 0.5f) + cys[c1] * 0.5f,
+                            mz = czs[c0] * (1.0f - 0.5f) + czs[c1] * 0.5f;
+                uint32_t kx = __float_as_uint(mx);
                 if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
                 bool won;
-                const uint32_t pos = hash_find_or_insert(table, table_mask, kx, ky, kz, 0xFFFFFFFEu, &won);
-                if (pos == 0xFFFFFFFFu) { atomicOr(&st->error_flags, ERR_HASH_FULL); continue; }
-                if (won) {
-                    // warp-aggregated allocation: one atomic per group of winning lanes, not one per vertex
-                    const cg::coalesced_group g = cg::coalesced_threads();
-                    uint32_t base = 0;
-                    if (g.thread_rank() == 0) base = atomicAdd(&st->n_uniq, (uint32_t) g.size());
-                    const uint32_t uid = g.shfl(base, 0) + g.thread_rank();
-                    if (uid < cap_uniq) {
-                        ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
-                    } else {
-                        atomicOr(&st->error_flags, ERR_UNIQ_CAP);
-                    }
-                    reinterpret_cast<uint32_t*>(table + pos)[3] = uid;   // readers come after the kernel boundary
-                }
+                const uint32_t pos = hash_find_or_insert(table, table_mask, kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &won);
+                if (pos == 0xFFFFFFFFu) full = true;
+                if (won) won_mask |= 1u << e;
                 eref[e] = pos;
             }
         }
-        const unsigned long long packed = mc.packed[cube_index];
-        const uint32_t t0 = tri_off[v];
-        for (uint32_t j = 0; j < 3 * ntri; j++) {
-            const int e = (int) ((packed >> (4 * j)) & 0xFull);
-            uint32_t r = 0xFFFFFFFFu;
+        if (__any_sync(0xffffffffu, full) && lane == 0) atomicOr(&st->error_flags, ERR_HASH_FULL);
+        // --- offsets: triangles and new vertex ids, both in list order
+        const uint32_t nwon = __popc(won_mask);
+        const uint32_t tri_incl = warp_inclusive_sum(ntri, lane), uid_incl = warp_inclusive_sum(nwon, lane);
+        const uint32_t tri_total = __shfl_sync(0xffffffffu, tri_incl, 31), uid_total = __shfl_sync(0xffffffffu, uid_incl, 31);
+        const uint32_t tri_base = warp_lookback(tiles_tri, tile, epoch_tri, tri_total);
+        const uint32_t uid_base = warp_lookback(tiles_uid, tile, epoch_uid, uid_total);
+        const bool fits = tri_base + tri_total <= cap_tris && uid_base + uid_total <= cap_uniq;
+        if (!fits && lane == 0) atomicOr(&st->error_flags, tri_base + tri_total > cap_tris ? ERR_TRI_CAP : ERR_UNIQ_CAP);
+        if (active) {
+            cases[v] = (uint8_t) cube_index;
+            const uint32_t t0 = tri_base + tri_incl - ntri;
+            tri_off[v] = t0;
+            if (fits && !full) {
+                uint32_t uid = uid_base + uid_incl - nwon;
 #pragma unroll
-            for (int q = 0; q < 12; q++) if (q == e) r = eref[q];
-            slot_ref[3 * (size_t) t0 + j] = r;
+                for (int e = 0; e < 12; e++) {
+                    if (won_mask & (1u << e)) {
+                        const int c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
+                        const int c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
+                        ustart[3 * (size_t) uid] = cxs[c0] * (1.0f - 0.5f) + cxs[c1] * 0.5f;
+                        ustart[3 * (size_t) uid + 1] = cys[c0] * (1.0f - 0.5f) + cys[c1] * 0.5f;
+                        ustart[3 * (size_t) uid + 2] = czs[c0] * (1.0f - 0.5f) + czs[c1] * 0.5f;
+                        reinterpret_cast<uint32_t*>(table + eref[e])[3] = uid;   // readers come after the kernel boundary
+                        uid++;
+                    }
+                }
+                const unsigned long long packed = mc.packed[cube_index];
+                for (uint32_t j = 0; j < 3 * ntri; j++) {
+                    const int e = (int) ((packed >> (4 * j)) & 0xFull);
+                    uint32_t r = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int q = 0; q < 12; q++) if (q == e) r = eref[q];
+                    slot_ref[3 * (size_t) t0 + j] = r;
+                }
+            }
+        }
+        if (tile == ntiles - 1 && lane == 0) {
+            st->n_tris_raw = min(tri_base + tri_total, cap_tris);
+            st->n_uniq = min(uid_base + uid_total, cap_uniq);
         }
     }
 }
 
-// closest_surface_point per distinct mid-point.  Lanes that finish pull the next vertex (warp-level refill from a
-// global ticket), so a warp's lanes stay busy although iteration counts differ per vertex.
+// Device-sized clears for the per-vertex / per-slot weld state (exactly as many entries as this mesh needs):
+//   first_slot[0, n_uniq) = 0xFFFFFFFF, first_bits[0, ceil(3T/32)) = 0, weld table[0, weld_table_size(n_uniq)) = EMPTY.
+__device__ __forceinline__ uint32_t weld_table_size(uint32_t n_uniq, uint32_t max_entries) {
+    uint32_t s = 1024;
+    while (s < 2u * n_uniq && s < max_entries) s <<= 1;
+    return s;
+}
+__global__ void __launch_bounds__(256) k_clear_weld_state(DevState* st, uint32_t* __restrict__ first_slot, uint32_t* __restrict__ first_bits,
+                                                          uint4* __restrict__ table2, uint32_t max_entries, uint32_t cap_uniq, int clear_first_slot) {
+    const uint32_t nu = min(st->n_uniq, cap_uniq), T = st->n_tris_raw;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (clear_first_slot)
+        for (uint32_t i = tid; i < nu; i += stride) first_slot[i] = 0xFFFFFFFFu;
+    const uint32_t nw = (3u * T + 31u) / 32u + 1u;
+    for (uint32_t i = tid; i < nw; i += stride) first_bits[i] = 0u;
+    const uint32_t ts = weld_table_size(nu, max_entries);
+    const uint4 empty = make_uint4(SDM_HASH_EMPTY, SDM_HASH_EMPTY, SDM_HASH_EMPTY, SDM_HASH_EMPTY);
+    for (uint32_t i = tid; i < ts; i += stride) table2[i] = empty;
+    if (tid == 0) { st->n_tris_out = 0; st->n_verts_out = 0; st->ticket[TK_SCAN_FIRST] = 0; st->ticket[TK_SCAN_TRI] = 0; st->ticket[TK_PROJECT] = 0; st->n_stragglers = 0; st->ticket[TK_TAIL] = 0; }
+}
+
+// closest_surface_point per distinct mid-point (signed_distance.cu:227-240), bulk phase: one lane per vertex; lanes that
+// finish pull the next vertex (warp-level refill from a global ticket), so a warp's lanes stay busy although iteration
+// counts differ.  A vertex that is still running after SDM_NEWTON_BULK_ITERS iterations is handed, with its state, to
+// k_project_tail: the reference allows up to 10 000 iterations, and a lone slow lane would otherwise pin a whole warp
+// (and drag its cell's primitives into the warp's mask) for thousands of latency-bound steps.
+#define SDM_NEWTON_BULK_ITERS 40u
+struct Straggler { uint32_t uid, it; float g[3]; float s[3]; uint32_t power, lam, stop_at, pad; };   // 48 B: vertex, iterate, Brent state
+
 __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart,
-                                                 float* __restrict__ upos, uint32_t cap_uniq, MaskGrid grid) {
+                                                 float* __restrict__ upos, uint32_t cap_uniq, Straggler* __restrict__ stragglers,
+                                                 uint32_t cap_stragglers, MaskGrid grid) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags) return;
     bool have = false;
     uint32_t uid = 0, it = 0, iters_done = 0;
     float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -354,12 +373,74 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
                 upos[3 * (size_t) uid] = gx; upos[3 * (size_t) uid + 1] = gy; upos[3 * (size_t) uid + 2] = gz;
                 iters_done += it;
                 have = false;
+            } else if (it >= SDM_NEWTON_BULK_ITERS) {
+                const uint32_t slot = atomicAdd(&st->n_stragglers, 1u);
+                if (slot < cap_stragglers) {
+                    Straggler r;
+                    r.uid = uid; r.it = it; r.g[0] = gx; r.g[1] = gy; r.g[2] = gz;
+                    r.s[0] = cyc.sx; r.s[1] = cyc.sy; r.s[2] = cyc.sz; r.power = cyc.power; r.lam = cyc.lam;
+                    r.stop_at = cyc.stop_at; r.pad = 0;
+                    stragglers[slot] = r;
+                    iters_done += it;
+                    have = false;
+                } else {
+                    atomicSub(&st->n_stragglers, 1u);   // list full: keep iterating here
+                }
             }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) iters_done += __shfl_xor_sync(0xffffffffu, iters_done, o);
     if (lane == 0 && iters_done) atomicAdd(&st->newton_iters, (unsigned long long) iters_done);
+}
+
+// Tail phase: one WARP per straggler.  The 13 evaluation points of a Newton step (the iterate and the 12 stencil points
+// of empirical_normal) go to 13 lanes, so a step costs one evaluation's latency instead of thirteen; every lane then
+// forms the same update from the 13 shuffled values (identical arithmetic => identical bits in all lanes).
+__global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ scene, DevState* st, float* __restrict__ upos,
+                                                      const Straggler* __restrict__ stragglers, uint32_t cap_stragglers, MaskGrid grid) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = min(st->n_stragglers, cap_stragglers);
+    unsigned long long extra_iters = 0;
+    while (true) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&st->ticket[TK_TAIL], 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n) break;
+        const Straggler r = stragglers[idx];
+        float gx = r.g[0], gy = r.g[1], gz = r.g[2];
+        uint32_t it = r.it;
+        NewtonCycle cyc;
+        cyc.sx = r.s[0]; cyc.sy = r.s[1]; cyc.sz = r.s[2]; cyc.power = r.power; cyc.lam = r.lam; cyc.stop_at = r.stop_at;
+        bool collision = false;
+        while (!collision && it < cyc.stop_at) {
+            tile_mask_from_point(grid, sc, lane == 0, gx, gy, gz);
+            // lane 0: the iterate; lane 1 + 4*axis + s: stencil point s of that axis (same construction as normal_points)
+            float x = gx, y = gy, z = gz;
+            if (lane >= 1 && lane <= 12) {
+                const uint32_t q = lane - 1u, a = q >> 2, sidx = q & 3u;
+                const float o = sidx == 0 ? 2.0f * SDM_NORMAL_EPSILON : (sidx == 1 ? SDM_NORMAL_EPSILON : (sidx == 2 ? -SDM_NORMAL_EPSILON : -2.0f * SDM_NORMAL_EPSILON));
+                x = gx + (a == 0 ? o : 0.0f); y = gy + (a == 1 ? o : 0.0f); z = gz + (a == 2 ? o : 0.0f);
+            }
+            float fv = 0.0f;
+            if (lane <= 12) fv = eval_scene1(sc, x, y, z);
+            float f[13];
+#pragma unroll
+            for (int j = 0; j < 13; j++) f[j] = __shfl_sync(0xffffffffu, fv, j);
+            float nx, ny, nz;
+            normal_from_samples<1>(f, nx, ny, nz);
+            const float sd = f[0];
+            gx -= sd * nx; gy -= sd * ny; gz -= sd * nz;
+            collision = fabsf(sd) <= 0.00001f;
+            it++;
+            if (!collision) cyc.observe(gx, gy, gz, it);
+        }
+        if (lane == 0) { upos[3 * (size_t) r.uid] = gx; upos[3 * (size_t) r.uid + 1] = gy; upos[3 * (size_t) r.uid + 2] = gz; }
+        extra_iters += it - r.it;
+    }
+    if (lane == 0 && extra_iters) atomicAdd(&st->newton_iters, extra_iters);
 }
 
 __global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
@@ -442,9 +523,10 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
 // Weld, step 1: every vertex that is referenced by a kept triangle enters the key table with the smallest slot
 // id (3*triangle + corner, post-flip order) at which it occurs; the table keeps the minimum per key.
 __global__ void __launch_bounds__(256) k_weld_insert(DevState* st, const float* __restrict__ upos, const uint32_t* __restrict__ first_slot,
-                                                     uint4* table, uint32_t table_mask, uint32_t* __restrict__ wref, uint32_t cap_uniq) {
+                                                     uint4* table, uint32_t max_entries, uint32_t* __restrict__ wref, uint32_t cap_uniq) {
     const uint32_t n = min(st->n_uniq, cap_uniq);
     if (st->error_flags) return;
+    const uint32_t table_mask = weld_table_size(n, max_entries) - 1u;   // same size k_clear_weld_state cleared
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
         const uint32_t fs = first_slot[u];
         if (fs == 0xFFFFFFFFu) { wref[u] = 0xFFFFFFFFu; continue; }
