@@ -219,7 +219,7 @@ namespace {
 // dynamic shared memory: the scene blob, then one primitive mask per warp when culling is on
 size_t smem_for(const SdmHandle* h, int threads = 256) {
     size_t b = (size_t) h->scene_bytes;
-    if (h->mask_capable) b += (size_t) (threads / 32) * ((h->scene_nprims + 31) / 32) * 4;
+    if (h->mask_capable) b += (size_t) (threads / 32) * cull_smem_per_warp((h->scene_nprims + 31) / 32);
     return (b + 15) & ~(size_t) 15;
 }
 
@@ -1084,6 +1084,8 @@ int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes) {
     else if (n == "tri_uid") { src = h->tri_uid.p; have = h->tri_uid.n * 4; }
     else if (n == "tri_off") { src = h->tri_off.p; have = h->tri_off.n * 4; }
     else if (n == "first_slot") { src = h->first_slot.p; have = h->first_slot.n * 4; }
+    else if (n == "masks_fine") { src = h->masks_fine.p; have = h->masks_fine.n * 4; }
+    else if (n == "masks_coarse") { src = h->masks_coarse.p; have = h->masks_coarse.n * 4; }
     else return fail(SDM_ERR_INVALID, "unknown buffer name");
     if (bytes > have) return fail(SDM_ERR_INVALID, "buffer smaller than requested");
     CK(cudaStreamSynchronize(h->stream));

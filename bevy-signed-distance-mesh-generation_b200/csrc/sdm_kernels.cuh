@@ -346,24 +346,35 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
     float gx = 0.f, gy = 0.f, gz = 0.f;
     NewtonCycle cyc;
     cyc.start(0.f, 0.f, 0.f);
+    // Vertices are taken in chunks of consecutive ids (consecutive ids are spatial neighbours, k_classify_edges), one chunk
+    // per warp at a time: the lanes of a warp then work in one neighbourhood, which keeps the tile's primitive list short.
+    const uint32_t CHUNK = 256u;
+    uint32_t chunk_next = 0, chunk_end = 0;
     bool drained = false;
     while (true) {
         const uint32_t need = __ballot_sync(0xffffffffu, !have);
-        if (need && !drained) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&st->ticket[TK_PROJECT], (uint32_t) __popc(need));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!have) {
-                const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
-                if (idx < n) {
+        if (need) {
+            if (chunk_next >= chunk_end && !drained) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&st->ticket[TK_PROJECT], CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) drained = true;
+                else { chunk_next = base; chunk_end = min(base + CHUNK, n); }
+            }
+            if (chunk_next < chunk_end) {
+                const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
+                if (!have && idx < chunk_end) {
                     uid = idx; it = 0; have = true;
                     gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
                     cyc.start(gx, gy, gz);
                 }
+                chunk_next = min(chunk_next + (uint32_t) __popc(need), chunk_end);
             }
-            if (base + __popc(need) >= n) drained = true;
         }
-        if (!__any_sync(0xffffffffu, have)) break;
+        if (!__any_sync(0xffffffffu, have)) {
+            if (drained) break;
+            continue;   // chunk boundary: fetch the next chunk
+        }
         tile_mask_from_point(grid, sc, have, gx, gy, gz);   // cells of the lanes' current iterates
         if (have) {
             const bool collision = newton_step(sc, gx, gy, gz);
