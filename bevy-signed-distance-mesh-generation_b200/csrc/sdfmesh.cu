@@ -405,6 +405,7 @@ int enqueue_mesh_local(SdmHandle* h) {
     CK(cudaMemsetAsync(&h->state.p->n_tris_raw, 0, offsetof(DevState, error_flags) - offsetof(DevState, n_tris_raw), s));
     CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY + 1), s));   // + n_stragglers
     CK(cudaMemsetAsync(&h->state.p->newton_iters, 0, sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(&h->state.p->cull_tiles, 0, 4 * sizeof(unsigned long long), s));
     // vertex de-duplication table: sized from the previous mesh of this handle (4x its vertex count), full size at first;
     // an overflow is detected (ERR_HASH_FULL) and retried with the full table
     CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table1_entries * 16, s));
@@ -479,6 +480,9 @@ void fill_stats(SdmHandle* h, bool meshed) {
     for (int l = 0; l < h->level; l++) evals += 27ull * st.level_count[l];
     if (meshed) evals += 8ull * st.level_count[h->level] + 13ull * st.newton_iters + 12ull * st.n_uniq + 12ull * st.n_tris_raw;
     h->stats.sdf_evals = evals;
+    if (meshed && getenv("SDM_CULL_STATS") && st.cull_tiles)
+        fprintf(stderr, "[sdfmesh] orient tiles %llu: cell-union candidates/tile %.1f, refined list/tile %.1f, fallbacks %llu\n", st.cull_tiles,
+                (double) st.cull_cands / st.cull_tiles, (double) st.cull_prims / std::max<unsigned long long>(st.cull_tiles - st.cull_fallbacks, 1), st.cull_fallbacks);
 }
 
 void mesh_view(SdmHandle* h, SdmMesh* m) {
@@ -1090,6 +1094,24 @@ int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes) {
     if (bytes > have) return fail(SDM_ERR_INVALID, "buffer smaller than requested");
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SDM_OK;
+}
+
+// GPU self-test of the branch-free sqrt / division used by the culled fold: out[0] = sqrt mismatches over all 2^32 bit
+// patterns (must be 0), out[1] = patterns sent to the slow path, out[2] = division mismatches over `div_samples` random
+// (t, k) pairs (must be 0), out[3] = pairs sent to the slow path.
+int sdm_selftest_math(SdmHandle* h, unsigned long long div_samples, unsigned long long* out4) {
+    if (!h || !out4) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 32));
+    CK(cudaMemsetAsync(d, 0, 32, h->stream));
+    k_selftest_math<<<h->num_sms * 8, 256, 0, h->stream>>>(d, div_samples);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out4, d, 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
     return SDM_OK;
 }
 

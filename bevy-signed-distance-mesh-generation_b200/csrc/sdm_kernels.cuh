@@ -40,6 +40,7 @@ struct DevState {
     uint32_t error_flags;
     uint32_t ticket[TK_COUNT];
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
+    unsigned long long cull_tiles, cull_prims, cull_cands, cull_fallbacks;   // k_orient's tile culling statistics
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
 };
 
@@ -348,7 +349,9 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
     cyc.start(0.f, 0.f, 0.f);
     // Vertices are taken in chunks of consecutive ids (consecutive ids are spatial neighbours, k_classify_edges), one chunk
     // per warp at a time: the lanes of a warp then work in one neighbourhood, which keeps the tile's primitive list short.
-    const uint32_t CHUNK = 256u;
+    // chunk size: large enough for coherence, small enough that every warp gets >= ~4 chunks (load balance)
+    const uint32_t warps_in_grid = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t CHUNK = min(256u, max(32u, ((n / (warps_in_grid * 4u) + 31u) >> 5) << 5));
     uint32_t chunk_next = 0, chunk_end = 0;
     bool drained = false;
     while (true) {
@@ -505,6 +508,14 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
             mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f; my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f; mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
         }
         tile_mask_from_point(grid, sc, t < T, mx, my, mz);
+        if (sc.wmask && lane == 0) {   // statistics (one atomic per 32 triangles)
+            const uint32_t tc = *sc.tcount;
+            uint32_t cands = 0;
+            for (uint32_t w = 0; w < sc.W; w++) cands += __popc(sc.wmask[w]);
+            atomicAdd(&st->cull_tiles, 1ull);
+            atomicAdd(&st->cull_cands, (unsigned long long) cands);
+            if (tc == SDM_TLIST_NONE) atomicAdd(&st->cull_fallbacks, 1ull); else atomicAdd(&st->cull_prims, (unsigned long long) tc);
+        }
         if (t < T) {
             // normalize(cross(v1 - v0, v2 - v0))   (:103)
             const float ax = v[1][0] - v[0][0], ay = v[1][1] - v[0][1], az = v[1][2] - v[0][2];
@@ -784,6 +795,36 @@ __global__ void __launch_bounds__(128) k_eval_project(const uint4* __restrict__ 
             if (iters) iters[i] = collision ? it : 10000u;   // the reference's iteration count
         }
     }
+}
+
+// Exhaustive / randomised comparison of the branch-free sqrt and division with sqrtf and `/` (sdm_selftest_math).
+__global__ void __launch_bounds__(256) k_selftest_math(unsigned long long* __restrict__ out /* {sqrt mismatches, sqrt fallbacks, div mismatches, div fallbacks} */,
+                                                       unsigned long long div_samples) {
+    unsigned long long sm = 0, sf = 0, dm = 0, df = 0;
+    const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = tid; i < (1ull << 32); i += stride) {
+        const float x = __uint_as_float((uint32_t) i);
+        bool bad = false;
+        const float a = sqrt_nobranch(x, bad);
+        if (bad) { sf++; continue; }
+        const float b = sqrtf(x);
+        if (__float_as_uint(a) != __float_as_uint(b) && !(x == 0.0f)) sm++;
+    }
+    for (unsigned long long i = tid; i < div_samples; i += stride) {
+        // k log-uniform in [1e-6, 1e6] plus the scenes' own 0.1 / 0.5; t = k * u, u in (0, 1]
+        uint32_t r0 = (uint32_t) (i * 0x9E3779B97F4A7C15ull >> 32), r1 = (uint32_t) ((i ^ 0xD1B54A32D192ED03ull) * 0xBF58476D1CE4E5B9ull >> 32);
+        r0 ^= r0 >> 15; r0 *= 0x2C1B3C6Du; r0 ^= r0 >> 12; r1 ^= r1 >> 13; r1 *= 0x297A2D39u; r1 ^= r1 >> 15;
+        float k = (i & 3ull) == 0 ? 0.1f : ((i & 3ull) == 1 ? 0.5f : __uint_as_float(0x358637BDu + r0 % (0x49742400u - 0x358637BDu)));
+        const float u = (float) (r1 >> 8) * (1.0f / 16777216.0f);
+        const float t = (i & 4ull) ? k * u : __uint_as_float(r1 & 0x7FFFFFFFu);   // also arbitrary positive numerators
+        if (!(t > 0.0f) || !(t <= 1e30f)) continue;
+        if (t < SDM_DIV_GUARD_LO) { df++; continue; }
+        const float y = div_prepare(k);
+        const float a = div_nobranch(t, k, y);
+        const float b = t / k;
+        if (__float_as_uint(a) != __float_as_uint(b)) dm++;
+    }
+    atomicAdd(out + 0, sm); atomicAdd(out + 1, sf); atomicAdd(out + 2, dm); atomicAdd(out + 3, df);
 }
 
 // ---- primitive masks --------------------------------------------------------------------------------------

@@ -204,6 +204,10 @@ int sdm_get_stats(SdmHandle* h, SdmStats* out);
 /* Per-kernel timing for the bench's roofline line: when enabled, sdm_remesh records a CUDA event on the handle's
  * stream after every kernel it enqueues; sdm_get_kernel_times returns (name, ms) per kernel of the last remesh. */
 int sdm_set_profiling(SdmHandle* h, int enabled);
+/* GPU self-test of the branch-free IEEE sqrt / division of the culled fold (csrc/sdm_device.cuh): out4 = {sqrt
+ * mismatches over all 2^32 bit patterns, sqrt patterns sent to the slow path, division mismatches over div_samples
+ * random pairs, pairs sent to the slow path}.  Mismatch counts must be 0. */
+int sdm_selftest_math(SdmHandle* h, unsigned long long div_samples, unsigned long long* out4);
 /* Test access to intermediate device buffers of the last mesh stage ("ustart", "upos", "unrm", "tri_uid", "tri_off",
  * "first_slot"): copies `bytes` bytes to host memory. */
 int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes);

@@ -127,3 +127,12 @@ def test_newton_tail_cycle_detection_is_exact(handler, oracle_mod):
     # and the oracle itself still says so (fixture not stale)
     want, wit = oracle_mod.Oracle(scene).project(pts[-6:])
     assert np.array_equal(bits(want), bits(np.ascontiguousarray(exp[-6:, :3])))
+
+
+def test_branch_free_sqrt_and_division_are_ieee(handler):
+    """The culled fold uses branch-free copies of the library's sqrt / division fast paths; on the GPU they must agree
+    with sqrtf on ALL 2^32 bit patterns outside the guarded slow-path range, and with `/` on 2^32 random pairs."""
+    r = handler.selftest_math(1 << 32)
+    assert r["sqrt_mismatches"] == 0, r
+    assert r["div_mismatches"] == 0, r
+    assert r["sqrt_slow_path"] < (1 << 32) * 0.60   # negatives, NaN, denormal-range, huge: sent to sqrtf()
