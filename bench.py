@@ -43,11 +43,11 @@ WORKLOADS = {
     "c4_mandelbulb_2048": ("mandelbulb", 5.0, 128, 4, "BASELINE configs[3]: Mandelbulb, INIT 128 x 4 levels = 2048^3"),
     "c1_sphere_box_128": ("sphere_box", 5.0, 32, 2, "BASELINE configs[0]: sphere U box, INIT 32 x 2 levels = 128^3"),
 }
-DEFAULT_WORKLOAD = "sd_obj_1024"
+DEFAULT_WORKLOAD = "c3_many1024_1024"
 
 # Algorithmic FP32 operations per primitive evaluation (add/sub/mul/min/max/compare-select; sqrt and div counted as 1):
 # DESIGN.md "Algorithmic work".  Used only to convert evaluations/s into the roofline's TFLOP/s.
-OPS = {"capsule": 33, "sphere": 10, "box": 29, "smooth_min": 11, "min": 1, "mandelbulb": 25 * 60}
+OPS = {"capsule": 24, "sphere": 10, "box": 25, "smooth_min": 10, "min": 1, "mandelbulb": 25 * 60}
 
 
 def scene_ops_per_eval(scene: np.ndarray) -> int:
@@ -122,25 +122,19 @@ def make_scene(name):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU baseline: bounded sample of the same workload through the host-compiled reference / the oracle port
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(scene_name, scene, levels_lists, voxel_sizes, res, budget_s=15.0):
-    """levels_lists[l] = active list at level l (numpy), voxel_sizes[l] its voxel size.  Times the reference's refine
-    kernel on a sample of every level's parents and its mesh kernel + host weld on a sample of the final list, with
-    all host threads, and extrapolates each stage linearly in the number of voxels."""
+def cpu_sampled_remesh(scene_name, scene, bb, init, levels, res, budget_s=15.0, seed=0):
+    """Sampled descent, entirely on the host: at every level a random sample of the surviving voxels is refined with
+    the reference's refine kernel (timed), which also gives the survival ratio; at the finest level a sample is meshed
+    with the reference's mesh kernel and welded (timed).  Per-level voxel counts and the whole-remesh time are
+    extrapolated linearly from the samples.  Uses oracle/_ref/libref_host.so (the reference's own kernels, host-compiled)
+    for the sd_obj scene, the oracle port otherwise; all host threads."""
     from oracle import oracle as orc
 
     use_ref = scene_name == "sd_obj" and orc.RefHost.available()
     o = orc.Oracle(scene)
     ref = orc.RefHost() if use_ref else None
     threads = o.threads()
-
-    def sample_of(lst, k):
-        n = lst.shape[0]
-        if n <= k:
-            return lst
-        blocks = max(1, k // 64)
-        starts = np.linspace(0, n - 64, blocks).astype(np.int64)
-        idx = (starts[:, None] + np.arange(64)[None, :]).ravel()
-        return np.ascontiguousarray(lst[idx])
+    rng = np.random.default_rng(seed)
 
     def refine_fn(v, s):
         return ref.refine_raw(v, s) if use_ref else o.refine_raw(v, s)
@@ -148,53 +142,49 @@ def cpu_baseline_sample(scene_name, scene, levels_lists, voxel_sizes, res, budge
     def mesh_fn(v, s):
         return ref.mesh_raw(v, s) if use_ref else o.mesh_raw(v, s)[0]
 
+    def pick(lst, k):
+        if lst.shape[0] <= k:
+            return lst
+        return np.ascontiguousarray(lst[np.sort(rng.choice(lst.shape[0], k, replace=False))])
+
+    vox, vs = o.create_voxel_field(bb, init)
+    est_count = float(vox.shape[0])
     total = 0.0
     parts = []
-    L = len(levels_lists) - 1
-    # calibrate the mesh stage, which dominates
-    final = levels_lists[L]
-    probe = sample_of(final, 1024)
-    t = time.perf_counter(); mesh_fn(probe, voxel_sizes[L]); rate = probe.shape[0] / max(time.perf_counter() - t, 1e-6)
-    k_mesh = int(min(final.shape[0], max(2048, rate * budget_s * 0.7)))
-    smp = sample_of(final, k_mesh)
-    t = time.perf_counter(); tris = mesh_fn(smp, voxel_sizes[L]); t_mesh = time.perf_counter() - t
-    t = time.perf_counter(); pos, nrm, idx = o.weld(tris); t_weld = time.perf_counter() - t
-    scale = final.shape[0] / max(smp.shape[0], 1)
-    total += (t_mesh + t_weld) * scale
-    parts.append(f"mesh kernel+weld on {smp.shape[0]}/{final.shape[0]} final-level voxels ({t_mesh + t_weld:.2f}s)")
-    sample_tris = int(idx.shape[0])
-    per_level_budget = budget_s * 0.3 / max(L, 1)
-    for l in range(L):
-        lst = levels_lists[l]
-        probe = sample_of(lst, 2048)
-        t = time.perf_counter(); refine_fn(probe, voxel_sizes[l]); rate = probe.shape[0] / max(time.perf_counter() - t, 1e-6)
-        k = int(min(lst.shape[0], max(2048, rate * per_level_budget)))
-        smp_l = sample_of(lst, k)
-        t = time.perf_counter(); refine_fn(smp_l, voxel_sizes[l]); dt = time.perf_counter() - t
-        total += dt * lst.shape[0] / max(smp_l.shape[0], 1)
-        parts.append(f"refine L{l} on {smp_l.shape[0]}/{lst.shape[0]} ({dt:.2f}s)")
-    tri_total = sample_tris * scale
+    per_level_budget = budget_s * 0.35 / max(levels, 1)
+    for l in range(levels):
+        probe = pick(vox, 512)
+        t = time.perf_counter(); refine_fn(probe, vs); rate = probe.shape[0] / max(time.perf_counter() - t, 1e-6)
+        smp = pick(vox, int(max(4096, rate * per_level_budget)))
+        t = time.perf_counter(); raw = refine_fn(smp, vs); dt = time.perf_counter() - t
+        keep = np.isfinite(raw).all(axis=1)
+        children = raw[keep]
+        total += dt * est_count / smp.shape[0]
+        parts.append(f"refine L{l}: {smp.shape[0]} of ~{est_count:.0f} voxels in {dt:.2f}s")
+        est_count *= children.shape[0] / smp.shape[0]
+        vox, vs = np.ascontiguousarray(children), (vs / np.float32(2)).astype(np.float32)
+        if vox.shape[0] == 0:
+            break
+    tri_total = 0.0
+    if vox.shape[0]:
+        probe = pick(vox, 256)
+        t = time.perf_counter(); mesh_fn(probe, vs); rate = probe.shape[0] / max(time.perf_counter() - t, 1e-6)
+        smp = pick(vox, int(max(512, rate * budget_s * 0.6)))
+        t = time.perf_counter(); tris = mesh_fn(smp, vs); t_mesh = time.perf_counter() - t
+        t = time.perf_counter(); pos, nrm, idx = o.weld(tris); t_weld = time.perf_counter() - t
+        total += (t_mesh + t_weld) * est_count / smp.shape[0]
+        tri_total = idx.shape[0] * est_count / smp.shape[0]
+        parts.append(f"mesh kernel + weld: {smp.shape[0]} of ~{est_count:.0f} finest-level voxels in {t_mesh + t_weld:.2f}s")
     return {
         "value": float(res) ** 3 / total,
-        "unit": "effective SDF samples/s",
+        "unit": "samples/s",
         "cores": threads,
         "kind": "reference" if use_ref else "port",
-        "sample": "; ".join(parts) + "; stages extrapolated linearly in voxel count",
+        "sample": "sampled descent on the host; " + "; ".join(parts) + "; counts and times extrapolated linearly",
         "extrapolated_s_per_remesh": total,
+        "estimated_finest_voxels": est_count,
         "triangles_per_s": tri_total / total,
     }
-
-
-def collect_levels(handler, bb, init, levels):
-    lists, sizes = [], []
-    handler.field_reset(bb, init)
-    n, vs = handler.field_count()
-    lists.append(handler.field_download(n)); sizes.append(vs)
-    for _ in range(levels):
-        n = handler.field_refine()
-        _, vs = handler.field_count()
-        lists.append(handler.field_download(n)); sizes.append(vs)
-    return lists, sizes
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -291,17 +281,22 @@ def main():
     ops_per_eval = scene_ops_per_eval(scene)
     fp32_peak_tflops = 148 * 128 * sm_max_mhz * 1e6 / 1e12         # non-FMA: parity requires -fmad=false
     roofline = roofline_hbm = None
-    if "k_project" in kavg and rank == 0:
-        # evaluations of k_project = 13 per Newton iteration; iterations = (sdf_evals - other terms)
-        lc = st["level_counts"]
-        other = 27 * sum(lc[:levels]) + 8 * lc[levels] + 12 * st["unique_vertices"] + 12 * st["raw_triangles"]
-        proj_evals = st["sdf_evals"] - other
-        ach = proj_evals * ops_per_eval / (kavg["k_project"] * 1e-3) / 1e12
-        roofline = {"kernel": "k_project", "bound": "fp32", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+    if rank == 0 and kavg:
+        # dominant SDF kernel: achieved = (primitive, point) distance evaluations it actually folded (device counters, after
+        # culling) x algorithmic FP32 ops per such evaluation (scene average) / its CUDA-event time
+        pe = st["prim_evals"]
+        stage_of = {"k_refine": "refine", "k_classify_edges": "classify", "k_project": "project", "k_vertex_normals": "normals", "k_orient": "orient"}
+        cand = {k: v for k, v in kavg.items() if k in stage_of}
+        top = max(cand, key=cand.get)
+        nprims_compiled = sum(12 if int(p["kind"]) == 3 else 1 for p in scene)
+        ops_pp = ops_per_eval / max(nprims_compiled, 1)
+        work = pe[stage_of[top]]
+        ach = work * ops_pp / (kavg[top] * 1e-3) / 1e12
+        roofline = {"kernel": top, "bound": "fp32", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                     "frac": ach / fp32_peak_tflops, "traffic": None,
                     "peak_source": f"148 SM x 128 FP32 lanes x {sm_max_mhz:.0f} MHz, one op per lane-cycle (no FMA: -fmad=false is part of the parity contract)",
-                    "algorithmic_ops_per_eval": ops_per_eval, "evals_per_launch": proj_evals, "avg_launch_ms": kavg["k_project"],
-                    "share_of_step": kavg["k_project"] / step_sum}
+                    "algorithmic_ops_per_prim_point": ops_pp, "prim_point_evals_per_launch": work, "avg_launch_ms": kavg[top],
+                    "share_of_step": kavg[top] / step_sum}
         emit_bytes = vert_count * (24 + 24 + 4 + 4 + 16) + tri_count * (12 + 12 + 3 * 24)
         if "k_emit_vertices" in kavg and "k_emit_indices" in kavg:
             t_emit = (kavg["k_emit_vertices"] + kavg["k_emit_indices"]) * 1e-3
@@ -325,15 +320,14 @@ def main():
                            parallelism=f"x-slab shards of the level-{runner.split_level} active list over {world} GPU(s), mesh shards gathered to rank 0 (NCCL)" if world > 1 else "1 GPU"),
             "triangles_per_s": tri_count * args.steps / elapsed, "triangles": tri_count, "vertices": vert_count,
             "gpu_ms_per_step": gpu_ms / args.steps, "sdf_evals_per_step": st["sdf_evals"], "sdf_evals_per_s": st["sdf_evals"] * args.steps / elapsed,
-            "level_counts": st["level_counts"][: levels + 1], "gpu_launches": launches, "clocks": clocks,
+            "level_counts": st["level_counts"][: levels + 1], "prim_point_evals_per_step": st["prim_evals"], "gpu_launches": launches, "clocks": clocks,
             "e2e": {"value": float(res) ** 3 * args.steps / e2e["elapsed"], "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["elapsed"] * 1e3 / args.steps},
             "kernel_ms": {k: round(v, 5) for k, v in kavg.items()},
             "roofline": roofline, "roofline_hbm": roofline_hbm,
         }
         if world == 1 and not args.no_cpu_baseline:
-            lists, sizes = collect_levels(h, bb, init, levels)
-            line["cpu_baseline"] = cpu_baseline_sample(scene_name, scene, lists, sizes, res)
+            line["cpu_baseline"] = cpu_sampled_remesh(scene_name, scene, bb, init, levels, res)
         print(json.dumps(line), flush=True)
     h.close()
     if dist is not None:
@@ -343,35 +337,17 @@ def main():
 
 def run_reference(args, scene_name, scene, bb, init, levels, res, metric, config):
     """--impl reference: the reference's own CPU code path for this workload (oracle/_ref for sd_obj, else the oracle
-    port), all host threads, each step a bounded sample of the workload extrapolated to a full remesh."""
+    port), all host threads; each step is one bounded sampled remesh (cpu_sampled_remesh) extrapolated to a full one."""
     from oracle import oracle as orc
 
     orc.build()
-    o = orc.Oracle(scene)
-    # level lists come from the CPU path itself (no GPU needed): refine with the CPU oracle; bounded by working at the
-    # levels' true lists (refine is ~5% of the cost)
-    use_ref = scene_name == "sd_obj" and orc.RefHost.available()
-    ref = orc.RefHost() if use_ref else None
-    vox, vs = o.create_voxel_field(bb, init)
-    lists, sizes = [vox], [vs]
-    t_refine_full = 0.0
-    for _ in range(levels):
-        t = time.perf_counter()
-        raw = ref.refine_raw(vox, vs) if use_ref else o.refine_raw(vox, vs)
-        keep = np.isfinite(raw).all(axis=1)
-        vox, vs = raw[keep].copy(), (vs / np.float32(2)).astype(np.float32)
-        t_refine_full += time.perf_counter() - t
-        lists.append(vox); sizes.append(vs)
     steps = max(1, min(args.steps, 3))
-    results = []
-    for i in range(max(0, min(args.warmup, 1)) + steps):
-        r = cpu_baseline_sample(scene_name, scene, lists, sizes, res, budget_s=12.0)
-        results.append(r)
+    warm = 1 if args.warmup > 0 else 0
+    results = [cpu_sampled_remesh(scene_name, scene, bb, init, levels, res, budget_s=12.0, seed=i) for i in range(warm + steps)]
     r = results[-1]
-    vals = [x["value"] for x in results[-steps:]]
-    value = float(np.mean(vals))
+    value = float(np.mean([x["value"] for x in results[-steps:]]))
     line = {
-        "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": float(res) ** 3 / value * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic procedural scene (analytic SDF); no dataset", "config": config,
         "triangles_per_s": r["triangles_per_s"],

@@ -406,6 +406,7 @@ int enqueue_mesh_local(SdmHandle* h) {
     CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY + 1), s));   // + n_stragglers
     CK(cudaMemsetAsync(&h->state.p->newton_iters, 0, sizeof(unsigned long long), s));
     CK(cudaMemsetAsync(&h->state.p->cull_tiles, 0, 4 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(&h->state.p->prim_evals[WK_CLASSIFY], 0, 5 * sizeof(unsigned long long), s));   // refine's counter is reset with the field
     // vertex de-duplication table: sized from the previous mesh of this handle (4x its vertex count), full size at first;
     // an overflow is detected (ERR_HASH_FULL) and retried with the full table
     CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table1_entries * 16, s));
@@ -480,9 +481,7 @@ void fill_stats(SdmHandle* h, bool meshed) {
     for (int l = 0; l < h->level; l++) evals += 27ull * st.level_count[l];
     if (meshed) evals += 8ull * st.level_count[h->level] + 13ull * st.newton_iters + 12ull * st.n_uniq + 12ull * st.n_tris_raw;
     h->stats.sdf_evals = evals;
-    if (meshed && getenv("SDM_CULL_STATS") && st.cull_tiles)
-        fprintf(stderr, "[sdfmesh] orient tiles %llu: cell-union candidates/tile %.1f, refined list/tile %.1f, fallbacks %llu\n", st.cull_tiles,
-                (double) st.cull_cands / st.cull_tiles, (double) st.cull_prims / std::max<unsigned long long>(st.cull_tiles - st.cull_fallbacks, 1), st.cull_fallbacks);
+    for (int i = 0; i < 6; i++) h->stats.prim_evals[i] = st.prim_evals[i];
 }
 
 void mesh_view(SdmHandle* h, SdmMesh* m) {

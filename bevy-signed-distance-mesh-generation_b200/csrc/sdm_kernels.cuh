@@ -41,6 +41,7 @@ struct DevState {
     uint32_t ticket[TK_COUNT];
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
     unsigned long long cull_tiles, cull_prims, cull_cands, cull_fallbacks;   // k_orient's tile culling statistics
+    unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
 };
 
@@ -98,6 +99,17 @@ __device__ __forceinline__ constexpr uint32_t child_mask(int i, int j, int k) {
     return m;
 }
 
+// primitives one evaluation folds in the current tile (for the work counters)
+__device__ __forceinline__ uint32_t tile_prims(const SceneView& sc) {
+    if (!sc.wmask) return sc.nprims;
+    const uint32_t tc = *sc.tcount;
+    if (tc != SDM_TLIST_NONE) return tc;
+    uint32_t c = 0;
+    for (uint32_t w = 0; w < sc.W; w++) c += __popc(sc.wmask[w]);
+    return c;
+}
+enum WorkKind : int { WK_REFINE = 0, WK_CLASSIFY = 1, WK_PROJECT = 2, WK_TAIL = 3, WK_NORMALS = 4, WK_ORIENT = 5 };
+
 __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -121,12 +133,14 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
+    unsigned long long work = 0;
     while (true) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(&st->ticket[TK_REFINE0 + level], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) {
             if (tile == 0 && lane == 0) st->level_count[level + 1] = 0;   // empty input: no-op (src/cuda/mod.rs:137)
+            if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_REFINE], work);
             break;
         }
         const uint32_t p0 = tile << 5;
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
         }
         // primitives that can matter anywhere inside this tile's parent voxels (edge = 2 * child size)
         tile_mask_from_box(grid, sc, active, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
+        work += (unsigned long long) tile_prims(sc) * 27u * np;
         uint32_t m27 = 0;
         if (active) {
 #pragma unroll 1
@@ -213,12 +228,14 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
+    unsigned long long work = 0;
     while (true) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) {
             if (tile == 0 && lane == 0) { st->n_tris_raw = 0; st->n_uniq = 0; }
+            if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_CLASSIFY], work);
             break;
         }
         const uint32_t v = (tile << 5) + lane;
@@ -226,6 +243,7 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
         float bx = 0.f, by = 0.f, bz = 0.f;
         if (active) { bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2]; }
         tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
+        work += (unsigned long long) tile_prims(sc) * 8u * min(32u, n - (tile << 5));
         float cxs[8], cys[8], czs[8];
         uint32_t cube_index = 0;
         if (active) {
@@ -344,6 +362,7 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
     if (st->error_flags) return;
     bool have = false;
     uint32_t uid = 0, it = 0, iters_done = 0;
+    unsigned long long work = 0;
     float gx = 0.f, gy = 0.f, gz = 0.f;
     NewtonCycle cyc;
     cyc.start(0.f, 0.f, 0.f);
@@ -379,6 +398,7 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
             continue;   // chunk boundary: fetch the next chunk
         }
         tile_mask_from_point(grid, sc, have, gx, gy, gz);   // cells of the lanes' current iterates
+        work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, have));
         if (have) {
             const bool collision = newton_step(sc, gx, gy, gz);
             it++;
@@ -406,6 +426,7 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) iters_done += __shfl_xor_sync(0xffffffffu, iters_done, o);
     if (lane == 0 && iters_done) atomicAdd(&st->newton_iters, (unsigned long long) iters_done);
+    if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_PROJECT], work);
 }
 
 // Tail phase: one WARP per straggler.  The 13 evaluation points of a Newton step (the iterate and the 12 stencil points
@@ -417,7 +438,7 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(st->n_stragglers, cap_stragglers);
-    unsigned long long extra_iters = 0;
+    unsigned long long extra_iters = 0, work = 0;
     while (true) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(&st->ticket[TK_TAIL], 1u);
@@ -431,6 +452,7 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
         bool collision = false;
         while (!collision && it < cyc.stop_at) {
             tile_mask_from_point(grid, sc, lane == 0, gx, gy, gz);
+            work += (unsigned long long) tile_prims(sc) * 13u;
             // lane 0: the iterate; lane 1 + 4*axis + s: stencil point s of that axis (same construction as normal_points)
             float x = gx, y = gy, z = gz;
             if (lane >= 1 && lane <= 12) {
@@ -455,6 +477,7 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
         extra_iters += it - r.it;
     }
     if (lane == 0 && extra_iters) atomicAdd(&st->newton_iters, extra_iters);
+    if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_TAIL], work);
 }
 
 __global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
@@ -465,18 +488,21 @@ __global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict_
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long work = 0;
     for (uint32_t u0 = warp_id << 5; u0 < n; u0 += warps_total << 5) {   // warp-uniform trip count (tile masks are warp collectives)
         const uint32_t u = u0 + lane;
         const bool active = u < n;
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
         tile_mask_from_point(grid, sc, active, x, y, z);
+        work += (unsigned long long) tile_prims(sc) * 12u * min(32u, n - u0);
         if (active) {
             float nx, ny, nz;
             empirical_normal(sc, x, y, z, nx, ny, nz);
             unrm[3 * (size_t) u] = nx; unrm[3 * (size_t) u + 1] = ny; unrm[3 * (size_t) u + 2] = nz;
         }
     }
+    if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_NORMALS], work);
 }
 
 // Per raw triangle: orientation test and the reference host's triangle filter.
@@ -492,6 +518,7 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
     // warp-contiguous mapping so that one lane can write the 32 validity bits of a warp's triangles
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long work = 0;
     for (uint32_t t0 = warp_id << 5; t0 < T; t0 += warps_total << 5) {
         const uint32_t t = t0 + lane;
         bool valid = false;
@@ -508,14 +535,7 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
             mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f; my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f; mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
         }
         tile_mask_from_point(grid, sc, t < T, mx, my, mz);
-        if (sc.wmask && lane == 0) {   // statistics (one atomic per 32 triangles)
-            const uint32_t tc = *sc.tcount;
-            uint32_t cands = 0;
-            for (uint32_t w = 0; w < sc.W; w++) cands += __popc(sc.wmask[w]);
-            atomicAdd(&st->cull_tiles, 1ull);
-            atomicAdd(&st->cull_cands, (unsigned long long) cands);
-            if (tc == SDM_TLIST_NONE) atomicAdd(&st->cull_fallbacks, 1ull); else atomicAdd(&st->cull_prims, (unsigned long long) tc);
-        }
+        work += (unsigned long long) tile_prims(sc) * 12u * min(32u, T - t0);
         if (t < T) {
             // normalize(cross(v1 - v0, v2 - v0))   (:103)
             const float ax = v[1][0] - v[0][0], ay = v[1][1] - v[0][1], az = v[1][2] - v[0][2];
@@ -540,6 +560,7 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
         const uint32_t bits = __ballot_sync(0xffffffffu, valid);
         if (lane == 0) tri_valid_bits[t0 >> 5] = bits;
     }
+    if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_ORIENT], work);
 }
 
 // Weld, step 1: every vertex that is referenced by a kept triangle enters the key table with the smallest slot

@@ -57,7 +57,7 @@ class _Stats(ctypes.Structure):
     _fields_ = [
         ("kernel_launches", ctypes.c_uint64), ("sdf_evals", ctypes.c_uint64), ("level_counts", ctypes.c_uint32 * 16),
         ("unique_vertices", ctypes.c_uint32), ("raw_triangles", ctypes.c_uint32), ("last_gpu_ms", ctypes.c_float),
-        ("reserved", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32), ("prim_evals", ctypes.c_uint64 * 6),
     ]
 
 
@@ -352,4 +352,5 @@ class CudaHandler:
         s = _Stats()
         self._check(self._lib.sdm_get_stats(self._h, ctypes.byref(s)))
         return dict(kernel_launches=int(s.kernel_launches), sdf_evals=int(s.sdf_evals), level_counts=list(s.level_counts),
-                    unique_vertices=int(s.unique_vertices), raw_triangles=int(s.raw_triangles), last_gpu_ms=float(s.last_gpu_ms))
+                    unique_vertices=int(s.unique_vertices), raw_triangles=int(s.raw_triangles), last_gpu_ms=float(s.last_gpu_ms),
+                    prim_evals=dict(zip(("refine", "classify", "project", "tail", "normals", "orient"), [int(x) for x in s.prim_evals])))

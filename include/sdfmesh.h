@@ -199,6 +199,8 @@ typedef struct SdmStats {
     uint32_t raw_triangles;        /* triangles before the finite-vertex filter */
     float last_gpu_ms;             /* CUDA-event time of the last remesh / mesh call on the handle's stream */
     uint32_t reserved;
+    uint64_t prim_evals[6];        /* (primitive, point) distance evaluations actually folded by the last remesh, per stage:
+                                      refine, classify, project, project tail, vertex normals, orient (after culling) */
 } SdmStats;
 int sdm_get_stats(SdmHandle* h, SdmStats* out);
 /* Per-kernel timing for the bench's roofline line: when enabled, sdm_remesh records a CUDA event on the handle's
