@@ -64,14 +64,6 @@ __device__ __forceinline__ void stage_mc(McShared* s) {
     __syncthreads();
 }
 
-// corner c of a voxel (compute_mesh_generation.cu:77-86): +x iff c%4 in {1,2}, +y iff c%4 >= 2, +z iff c >= 4.
-// The zero is added too (v[0] += cond ? size : 0.0f), exactly as in the reference.
-__device__ __forceinline__ void voxel_corner(float bx, float by, float bz, float sx, float sy, float sz, int c, float& x, float& y, float& z) {
-    const int c4 = c & 3;
-    x = bx + ((c4 == 1 || c4 == 2) ? sx : 0.0f);
-    y = by + ((c4 >= 2) ? sy : 0.0f);
-    z = bz + ((c >= 4) ? sz : 0.0f);
-}
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_init_field(float* __restrict__ vox, DevState* st, float bb_size, uint32_t init, float size,
                                                     uint32_t cap_vox) {
@@ -88,15 +80,6 @@ __global__ void __launch_bounds__(256) k_init_field(float* __restrict__ vox, Dev
         vox[3 * i + 1] = (float) y * size - half;
         vox[3 * i + 2] = (float) z * size - half;
     }
-}
-
-// Corner masks of the 8 children inside the parent's 3x3x3 lattice; lattice index l = a*9 + b*3 + c (a: x, b: y, c: z).
-__device__ __forceinline__ constexpr uint32_t child_mask(int i, int j, int k) {
-    uint32_t m = 0;
-    for (int di = 0; di < 2; di++)
-        for (int dj = 0; dj < 2; dj++)
-            for (int dk = 0; dk < 2; dk++) m |= 1u << ((i + di) * 9 + (j + dj) * 3 + (k + dk));
-    return m;
 }
 
 // primitives one evaluation folds in the current tile (for the work counters)
