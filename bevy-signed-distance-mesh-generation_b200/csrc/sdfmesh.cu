@@ -173,6 +173,7 @@ struct SdmHandle {
     DevBuf<uint32_t> masks_fine, masks_coarse;
     MaskGrid grid {};                   // grid.enabled == 0 until ensure_masks has built it
     float grid_bb = 0.0f;
+    uint32_t grid_init = 0;
     uint32_t masks_built = 0;           // statistics: number of mask builds
 
     // field (ping-pong lists) and its host-known description
@@ -216,10 +217,12 @@ struct SdmHandle {
 
 namespace {
 
-// dynamic shared memory: the scene blob, then one primitive mask per warp when culling is on
-size_t smem_for(const SdmHandle* h, int threads = 256) {
-    size_t b = (size_t) h->scene_bytes;
-    if (h->mask_capable) b += (size_t) (threads / 32) * cull_smem_per_warp((h->scene_nprims + 31) / 32);
+// dynamic shared memory: culled scenes need one culling slot per warp (the table is read through L1); small scenes
+// stage the table.  k_build_masks always stages it (staged = true).
+size_t smem_for(const SdmHandle* h, int threads = 256, bool staged = false) {
+    size_t b;
+    if (h->mask_capable && !staged) b = (size_t) (threads / 32) * cull_smem_per_warp((h->scene_nprims + 31) / 32);
+    else b = (size_t) h->scene_bytes;
     return (b + 15) & ~(size_t) 15;
 }
 
@@ -250,7 +253,7 @@ void prof_end(SdmHandle* h) {   // after the stream has been synchronised
 }
 
 int configure_kernels(SdmHandle* h) {
-    if (smem_for(h, 256) > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
+    if (smem_for(h, 256, true) > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
     struct K { const void* f; int threads; int* grid; };
     const K ks[] = {
         { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify_edges, 256, &h->g_classify },
@@ -267,7 +270,7 @@ int configure_kernels(SdmHandle* h) {
     }
     for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project })
         CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 128), 1024)));
-    CK(cudaFuncSetAttribute((const void*) k_build_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 256), 1024)));
+    CK(cudaFuncSetAttribute((const void*) k_build_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 256, true), 1024)));
     h->g_light = h->num_sms * 8;
     return SDM_OK;
 }
@@ -292,7 +295,7 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     // radius = circumsphere of the cell cube (x1.0001) + the empirical_normal stencil reach (2e-3, signed_distance.cu:179)
     //          + slop for the inward-nudged box probes and the domain-face tolerance (2e-3 cell) + 1e-4
     auto rho = [](float cell) { return cell * 0.8660254f * 1.0001f + 0.0021f + 2e-3f * cell + 1e-4f; };
-    const size_t smem = smem_for(h, 256);
+    const size_t smem = smem_for(h, 256, true);
     k_build_masks<<<h->num_sms * 4, 256, smem, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell));
     k_build_masks<<<h->num_sms * 8, 256, smem, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell));
     mark(h, "k_build_masks_x2");
@@ -300,6 +303,7 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     CK(cudaGetLastError());
     h->grid = fine;
     h->grid_bb = bb_size;
+    h->grid_init = init_factor;
     h->masks_built++;
     return SDM_OK;
 }
@@ -360,6 +364,13 @@ int reset_state(SdmHandle* h) {
     return SDM_OK;
 }
 
+// culled scenes must never be launched without a grid (their kernels do not stage the table): rebuild over the last
+// domain, or the reference's default cube (bindings.h:9-10); points outside simply use the full list
+int ensure_masks_any(SdmHandle* h) {
+    if (!h->mask_capable || h->grid.enabled) return SDM_OK;
+    return ensure_masks(h, h->grid_bb > 0.0f ? h->grid_bb : SDM_MESH_GENERATION_BB_SIZE, h->grid_init ? h->grid_init : 64);
+}
+
 int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
     int mrc = ensure_masks(h, p.bb_size, p.init_factor);
     if (mrc) return mrc;
@@ -376,6 +387,8 @@ int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
 
 int enqueue_refine(SdmHandle* h) {
     if (h->level >= 15) return fail(SDM_ERR_INVALID, "too many refinement levels (max 15)");
+    int mrc = ensure_masks_any(h);
+    if (mrc) return mrc;
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
                                                                 next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz, h->grid);
@@ -397,6 +410,8 @@ int enqueue_weld_clears(SdmHandle* h, bool clear_first_slot) {
 
 // classify+edges -> project (+tail) -> normals -> orient: everything that needs only this handle's voxels
 int enqueue_mesh_local(SdmHandle* h) {
+    int mrc = ensure_masks_any(h);
+    if (mrc) return mrc;
     const float sx = h->voxel_size[0], sy = h->voxel_size[1], sz = h->voxel_size[2];
     const float* vox = h->vox[h->cur].p;
     const size_t smem = smem_for(h, 256), smem128 = smem_for(h, 128);
@@ -622,8 +637,8 @@ static int eval_common(SdmHandle* h, const float* points, uint32_t n, float* out
     if (iters) CK(cudaMalloc(&d_it, (size_t) n * 4));
     CK(cudaMemcpyAsync(d_in, points, (size_t) n * 12, cudaMemcpyHostToDevice, h->stream));
     const int grid = std::min<uint32_t>((n + 127) / 128, (uint32_t) h->num_sms * 8);
-    if (h->mask_capable && !h->grid.enabled) {   // probes outside a remesh: default domain (bindings.h:9-10)
-        int rc = ensure_masks(h, SDM_MESH_GENERATION_BB_SIZE, 64);
+    {   // probes outside a remesh: masks over the last / default domain
+        int rc = ensure_masks_any(h);
         if (rc) return rc;
     }
     if (which == 0) k_eval_sdf<<<grid, 128, smem_for(h, 128), h->stream>>>(h->scene.p, d_in, n, d_out, h->grid);
@@ -681,10 +696,8 @@ int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field) {
     if (rc) return rc;
     rc = reset_state(h);
     if (rc) return rc;
-    if (h->mask_capable && !h->grid.enabled) {   // an uploaded list carries no domain: masks over the default cube; points outside
-        rc = ensure_masks(h, SDM_MESH_GENERATION_BB_SIZE, 64);   // it simply use the full primitive list
-        if (rc) return rc;
-    }
+    rc = ensure_masks_any(h);   // an uploaded list carries no domain: masks over the last / default cube
+    if (rc) return rc;
     if (field->voxel_count)
         CK(cudaMemcpyAsync(h->vox[0].p, field->voxels, (size_t) field->voxel_count * 12, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(&h->state.p->level_count[0], &field->voxel_count, 4, cudaMemcpyHostToDevice, h->stream));
