@@ -193,6 +193,7 @@ struct SdmHandle {
     DevBuf<uint64_t> tiles, tiles2;
     DevBuf<Straggler> stragglers;
     uint32_t cap_stragglers = 0;
+    int cases_for_level = -1;           // level whose case indices the last k_refine wrote (-1: none)
     uint32_t table1_entries = 0;        // entries of table1 actually used (adaptive: sized from the previous mesh)
     DevBuf<DevState> state;
     DevState* host_state = nullptr;   // pinned
@@ -379,19 +380,24 @@ int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
     mark(h, "k_init_field");
     h->stats.kernel_launches++;
     h->cur = 0; h->level = 0;
+    h->cases_for_level = -1;
     h->voxel_size[0] = h->voxel_size[1] = h->voxel_size[2] = size;
     h->have_field = true;
     h->mesh_valid = false;
     return SDM_OK;
 }
 
-int enqueue_refine(SdmHandle* h) {
+// with_cases: this is the refinement right before a mesh stage - let it also write the children's case indices
+int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     if (h->level >= 15) return fail(SDM_ERR_INVALID, "too many refinement levels (max 15)");
     int mrc = ensure_masks_any(h);
     if (mrc) return mrc;
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
+    if (with_cases) cudaMemsetAsync(&h->state.p->cases_from_refine, 0, 4, h->stream);   // the kernel stores 2 if a lattice is inexact
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
-                                                                next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz, h->grid);
+                                                                next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz, h->grid,
+                                                                with_cases ? h->cases.p : nullptr);
+    h->cases_for_level = with_cases ? h->level + 1 : -1;
     mark(h, "k_refine");
     h->stats.kernel_launches++;
     h->cur ^= 1; h->level++;
@@ -429,7 +435,7 @@ int enqueue_mesh_local(SdmHandle* h) {
     const uint32_t e_tri = next_epoch(h), e_uid = next_epoch(h);
     k_classify_edges<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, e_tri, e_uid, h->tiles.p, h->tiles2.p, h->cases.p,
                                                        h->tri_off.p, h->cap_tris, h->table1.p, h->table1_entries - 1, h->ustart.p, h->cap_uniq,
-                                                       h->slot_ref.p, sx, sy, sz, h->grid);
+                                                       h->slot_ref.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? 1 : 0);
     mark(h, "k_classify_edges");
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
@@ -519,7 +525,7 @@ uint32_t grown(uint32_t cap) { return (uint32_t) std::min<uint64_t>((uint64_t) c
 
 // after a successful mesh: size the vertex table of the next mesh from this one
 void adapt_table1(SdmHandle* h) {
-    const uint32_t want = pow2_at_least(std::max<uint64_t>((uint64_t) h->host_state->n_uniq * 4, 1u << 16));
+    const uint32_t want = pow2_at_least(std::max<uint64_t>((uint64_t) h->host_state->n_uniq * 5 / 2, 1u << 16));
     h->table1_entries = std::min(want, h->table_entries);
 }
 // the adaptive vertex table was too small (and nothing else overflowed): retry with the full table, same capacities
@@ -702,6 +708,7 @@ int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field) {
         CK(cudaMemcpyAsync(h->vox[0].p, field->voxels, (size_t) field->voxel_count * 12, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(&h->state.p->level_count[0], &field->voxel_count, 4, cudaMemcpyHostToDevice, h->stream));
     h->cur = 0; h->level = 0;
+    h->cases_for_level = -1;
     h->voxel_size[0] = field->voxel_size.x; h->voxel_size[1] = field->voxel_size.y; h->voxel_size[2] = field->voxel_size.z;
     h->have_field = true; h->mesh_valid = false;
     CK(cudaStreamSynchronize(h->stream));   // the host list may be freed by the caller right after
@@ -867,7 +874,7 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
         rc = enqueue_init_field(h, p);
         if (rc) return rc;
         for (uint32_t l = 0; l < p.levels; l++) {
-            rc = enqueue_refine(h);
+            rc = enqueue_refine(h, l + 1 == p.levels);
             if (rc) return rc;
         }
         rc = enqueue_mesh(h);
@@ -982,7 +989,7 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
         h->stats.kernel_launches += 2;
         h->cur ^= 1;
         for (uint32_t l = split_level; l < p.levels; l++) {
-            rc = enqueue_refine(h);
+            rc = enqueue_refine(h, l + 1 == p.levels);
             if (rc) return rc;
         }
         rc = enqueue_mesh_local(h);

@@ -40,6 +40,8 @@ struct DevState {
     uint32_t error_flags;
     uint32_t ticket[TK_COUNT];
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
+    uint32_t cases_from_refine; // 0: the case indices written by the last k_refine are valid; 2: a parent's lattice was inexact
+    uint32_t pad1;
     unsigned long long cull_tiles, cull_prims, cull_cands, cull_fallbacks;   // k_orient's tile culling statistics
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
@@ -110,13 +112,15 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 // src/cuda/mod.rs:192) at the offset given by a warp scan + decoupled look-back across tiles.
 __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox,
                                                 float* __restrict__ out_vox, DevState* st, int level, uint32_t epoch,
-                                                uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz, MaskGrid grid) {
+                                                uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz, MaskGrid grid,
+                                                uint8_t* __restrict__ out_cases) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
     unsigned long long work = 0;
+    bool lattice_ok = true;
     while (true) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(&st->ticket[TK_REFINE0 + level], 1u);
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
         if (tile >= ntiles) {
             if (tile == 0 && lane == 0) st->level_count[level + 1] = 0;   // empty input: no-op (src/cuda/mod.rs:137)
             if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_REFINE], work);
+            if (out_cases && !__all_sync(0xffffffffu, lattice_ok) && lane == 0) st->cases_from_refine = 2u;
             break;
         }
         const uint32_t p0 = tile << 5;
@@ -172,12 +177,31 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
         if (excl_tile + total > cap_vox) {
             if (lane == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
         } else {
+            if (out_cases && active) {
+                // The mesh stage samples child corners at child_base + size (compute_mesh_generation.cu:77-86); the lattice
+                // has base + 2*size where the child is the upper one.  The 27 signs double as the children's corner signs
+                // only if both expressions give the same float on every axis (always true on the dyadic default grid).
+                lattice_ok = lattice_ok && __float_as_uint((bx + osx) + osx) == __float_as_uint(bx + 2.0f * osx) &&
+                             __float_as_uint((by + osy) + osy) == __float_as_uint(by + 2.0f * osy) &&
+                             __float_as_uint((bz + osz) + osz) == __float_as_uint(bz + 2.0f * osz);
+            }
 #pragma unroll
             for (int ch = 0; ch < 8; ch++) {
                 if (keep & (1u << ch)) {
                     out_vox[3 * (size_t) pos + 0] = bx + (float) (ch >> 2) * osx;
                     out_vox[3 * (size_t) pos + 1] = by + (float) ((ch >> 1) & 1) * osy;
                     out_vox[3 * (size_t) pos + 2] = bz + (float) (ch & 1) * osz;
+                    if (out_cases) {
+                        // cube_index bit c = sign at corner c: +x iff c%4 in {1,2}, +y iff c%4 >= 2, +z iff c >= 4
+                        uint32_t cube = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int dx = ((c & 3) == 1 || (c & 3) == 2) ? 1 : 0, dy = ((c & 3) >= 2) ? 1 : 0, dz = (c >= 4) ? 1 : 0;
+                            const int l = ((ch >> 2) + dx) * 9 + (((ch >> 1) & 1) + dy) * 3 + ((ch & 1) + dz);
+                            cube |= ((m27 >> l) & 1u) << c;
+                        }
+                        out_cases[pos] = (uint8_t) cube;
+                    }
                     pos++;
                 }
             }
@@ -201,7 +225,8 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
                                                         int level, uint32_t epoch_tri, uint32_t epoch_uid, uint64_t* tiles_tri, uint64_t* tiles_uid,
                                                         uint8_t* __restrict__ cases, uint32_t* __restrict__ tri_off, uint32_t cap_tris,
                                                         uint4* table, uint32_t table_mask, float* __restrict__ ustart, uint32_t cap_uniq,
-                                                        uint32_t* __restrict__ slot_ref, float sx, float sy, float sz, MaskGrid grid) {
+                                                        uint32_t* __restrict__ slot_ref, float sx, float sy, float sz, MaskGrid grid,
+                                                        int have_cases) {
     extern __shared__ uint4 smem[];
     __shared__ McShared mc;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -212,6 +237,8 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
     unsigned long long work = 0;
+    // case indices already written by the last k_refine (from its lattice signs)?  Then the 8 corner evaluations are skipped.
+    const bool reuse_cases = have_cases && st->cases_from_refine == 0u;
     while (true) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
@@ -225,17 +252,21 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
         const bool active = v < n;
         float bx = 0.f, by = 0.f, bz = 0.f;
         if (active) { bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2]; }
-        tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
-        work += (unsigned long long) tile_prims(sc) * 8u * min(32u, n - (tile << 5));
         float cxs[8], cys[8], czs[8];
         uint32_t cube_index = 0;
-        if (active) {
-            float f[8];
 #pragma unroll
-            for (int c = 0; c < 8; c++) voxel_corner(bx, by, bz, sx, sy, sz, c, cxs[c], cys[c], czs[c]);   // :77-86
-            eval_scene<8>(sc, cxs, cys, czs, f);
+        for (int c = 0; c < 8; c++) voxel_corner(bx, by, bz, sx, sy, sz, c, cxs[c], cys[c], czs[c]);   // :77-86
+        if (reuse_cases) {
+            if (active) cube_index = cases[v];
+        } else {
+            tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
+            work += (unsigned long long) tile_prims(sc) * 8u * min(32u, n - (tile << 5));
+            if (active) {
+                float f[8];
+                eval_scene<8>(sc, cxs, cys, czs, f);
 #pragma unroll
-            for (int c = 0; c < 8; c++) cube_index |= (uint32_t) (f[c] <= 0.0f) << c;   // marching_cubes.cu:22
+                for (int c = 0; c < 8; c++) cube_index |= (uint32_t) (f[c] <= 0.0f) << c;   // marching_cubes.cu:22
+            }
         }
         const uint32_t ntri = active ? mc.ntri[cube_index] : 0u;
         // --- edges: find-or-insert the mid-points; remember the table entry per edge and which ones this lane created
@@ -267,8 +298,8 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
         const uint32_t nwon = __popc(won_mask);
         const uint32_t tri_incl = warp_inclusive_sum(ntri, lane), uid_incl = warp_inclusive_sum(nwon, lane);
         const uint32_t tri_total = __shfl_sync(0xffffffffu, tri_incl, 31), uid_total = __shfl_sync(0xffffffffu, uid_incl, 31);
-        const uint32_t tri_base = warp_lookback(tiles_tri, tile, epoch_tri, tri_total);
-        const uint32_t uid_base = warp_lookback(tiles_uid, tile, epoch_uid, uid_total);
+        uint32_t tri_base, uid_base;
+        warp_lookback2(tiles_tri, tiles_uid, tile, epoch_tri, epoch_uid, tri_total, uid_total, tri_base, uid_base);
         const bool fits = tri_base + tri_total <= cap_tris && uid_base + uid_total <= cap_uniq;
         if (!fits && lane == 0) atomicOr(&st->error_flags, tri_base + tri_total > cap_tris ? ERR_TRI_CAP : ERR_UNIQ_CAP);
         if (active) {
