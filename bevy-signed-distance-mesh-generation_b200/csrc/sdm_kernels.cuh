@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
-    const uint32_t ntiles = (n + 31u) >> 5;
+    const uint32_t ntiles = (n + 31u) >> 5;   // warp-granular tiles: the heavy per-tile work hides the look-back walk here
     unsigned long long work = 0;
     bool lattice_ok = true;
     while (true) {
@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
         const uint32_t incl = warp_inclusive_sum(cnt, lane);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
+        const uint32_t block_end = excl_tile + total;
         uint32_t pos = excl_tile + incl - cnt;
-        if (excl_tile + total > cap_vox) {
+        if (block_end > cap_vox) {
             if (lane == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
         } else {
             if (out_cases && active) {
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
                 }
             }
         }
-        if (tile == ntiles - 1 && lane == 0) st->level_count[level + 1] = min(excl_tile + total, cap_vox);
+        if (tile == ntiles - 1 && lane == 0) st->level_count[level + 1] = min(block_end, cap_vox);
     }
 }
 
@@ -235,20 +236,23 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
     const SceneView sc = stage_scene_masked(scene, smem, grid);   // ends with __syncthreads
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
-    const uint32_t ntiles = (n + 31u) >> 5;
+    const uint32_t ntiles = (n + blockDim.x - 1u) / blockDim.x;   // block-granular tiles (see block_lookback)
     unsigned long long work = 0;
     // case indices already written by the last k_refine (from its lattice signs)?  Then the 8 corner evaluations are skipped.
     const bool reuse_cases = have_cases && st->cases_from_refine == 0u;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_w[66];
     while (true) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
         if (tile >= ntiles) {
-            if (tile == 0 && lane == 0) { st->n_tris_raw = 0; st->n_uniq = 0; }
+            if (tile == 0 && threadIdx.x == 0) { st->n_tris_raw = 0; st->n_uniq = 0; }
             if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_CLASSIFY], work);
             break;
         }
-        const uint32_t v = (tile << 5) + lane;
+        const uint32_t v = tile * blockDim.x + threadIdx.x;
         const bool active = v < n;
         float bx = 0.f, by = 0.f, bz = 0.f;
         if (active) { bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2]; }
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
             if (active) cube_index = cases[v];
         } else {
             tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
-            work += (unsigned long long) tile_prims(sc) * 8u * min(32u, n - (tile << 5));
+            work += (unsigned long long) tile_prims(sc) * 8u * (uint32_t) __popc(__ballot_sync(0xffffffffu, active));
             if (active) {
                 float f[8];
                 eval_scene<8>(sc, cxs, cys, czs, f);
@@ -298,10 +302,10 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
         const uint32_t nwon = __popc(won_mask);
         const uint32_t tri_incl = warp_inclusive_sum(ntri, lane), uid_incl = warp_inclusive_sum(nwon, lane);
         const uint32_t tri_total = __shfl_sync(0xffffffffu, tri_incl, 31), uid_total = __shfl_sync(0xffffffffu, uid_incl, 31);
-        uint32_t tri_base, uid_base;
-        warp_lookback2(tiles_tri, tiles_uid, tile, epoch_tri, epoch_uid, tri_total, uid_total, tri_base, uid_base);
-        const bool fits = tri_base + tri_total <= cap_tris && uid_base + uid_total <= cap_uniq;
-        if (!fits && lane == 0) atomicOr(&st->error_flags, tri_base + tri_total > cap_tris ? ERR_TRI_CAP : ERR_UNIQ_CAP);
+        uint32_t tri_base, uid_base, tri_end, uid_end;
+        block_lookback2(tiles_tri, tiles_uid, tile, epoch_tri, epoch_uid, tri_total, uid_total, s_w, tri_base, uid_base, tri_end, uid_end);
+        const bool fits = tri_end <= cap_tris && uid_end <= cap_uniq;
+        if (!fits && threadIdx.x == 0) atomicOr(&st->error_flags, tri_end > cap_tris ? ERR_TRI_CAP : ERR_UNIQ_CAP);
         if (active) {
             cases[v] = (uint8_t) cube_index;
             const uint32_t t0 = tri_base + tri_incl - ntri;
@@ -330,9 +334,9 @@ __global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict_
                 }
             }
         }
-        if (tile == ntiles - 1 && lane == 0) {
-            st->n_tris_raw = min(tri_base + tri_total, cap_tris);
-            st->n_uniq = min(uid_base + uid_total, cap_uniq);
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            st->n_tris_raw = min(tri_end, cap_tris);
+            st->n_uniq = min(uid_end, cap_uniq);
         }
     }
 }
@@ -384,32 +388,33 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
     // per warp at a time: the lanes of a warp then work in one neighbourhood, which keeps the tile's primitive list short.
     // chunk size: large enough for coherence, small enough that every warp gets >= ~4 chunks (load balance)
     const uint32_t warps_in_grid = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t CHUNK = min(256u, max(32u, ((n / (warps_in_grid * 4u) + 31u) >> 5) << 5));
+    const uint32_t CHUNK = sc.wmask ? min(256u, max(32u, ((n / (warps_in_grid * 4u) + 31u) >> 5) << 5)) : 32u;   // coherence only matters when culling
     uint32_t chunk_next = 0, chunk_end = 0;
     bool drained = false;
     while (true) {
-        const uint32_t need = __ballot_sync(0xffffffffu, !have);
-        if (need) {
-            if (chunk_next >= chunk_end && !drained) {
+        // refill idle lanes: from the warp's current chunk, and from a fresh chunk in the same round when that one runs out
+        for (int pass = 0; pass < 2; pass++) {
+            const uint32_t need = __ballot_sync(0xffffffffu, !have);
+            if (!need) break;
+            if (chunk_next >= chunk_end) {
+                if (drained) break;
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&st->ticket[TK_PROJECT], CHUNK);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n) drained = true;
-                else { chunk_next = base; chunk_end = min(base + CHUNK, n); }
+                if (base >= n) { drained = true; break; }
+                chunk_next = base; chunk_end = min(base + CHUNK, n);
             }
-            if (chunk_next < chunk_end) {
-                const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
-                if (!have && idx < chunk_end) {
-                    uid = idx; it = 0; have = true;
-                    gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
-                    cyc.start(gx, gy, gz);
-                }
-                chunk_next = min(chunk_next + (uint32_t) __popc(need), chunk_end);
+            const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
+            if (!have && idx < chunk_end) {
+                uid = idx; it = 0; have = true;
+                gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
+                cyc.start(gx, gy, gz);
             }
+            chunk_next = min(chunk_next + (uint32_t) __popc(need), chunk_end);
         }
         if (!__any_sync(0xffffffffu, have)) {
-            if (drained) break;
-            continue;   // chunk boundary: fetch the next chunk
+            if (drained || chunk_next >= chunk_end) { if (drained) break; }
+            continue;   // fetch the next chunk
         }
         tile_mask_from_point(grid, sc, have, gx, gy, gz);   // cells of the lanes' current iterates
         work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, have));
