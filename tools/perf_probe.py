@@ -14,6 +14,10 @@ def run(name, scene, bb, init, levels, reps=3):
     st = h.stats()
     print(f"== {name}: res {init << levels}^3 voxels {st['level_counts'][:levels+1]} tris {m.triangle_count} verts {m.vertex_count} uniq {st['unique_vertices']} "
           f"gpu {st['last_gpu_ms']:.3f} ms wall {wall*1e3:.3f} ms evals {st['sdf_evals']/1e6:.1f}M -> {st['sdf_evals']/st['last_gpu_ms']/1e6:.2f} Gevals/s")
+    pe = st["prim_evals"]; lc = st["level_counts"]
+    ev = dict(refine=27 * sum(lc[:levels]), classify=8 * lc[levels], normals=12 * st["unique_vertices"], orient=12 * st["raw_triangles"])
+    ev["project"] = st["sdf_evals"] - sum(ev.values())
+    print("     primitives folded per evaluation: " + ", ".join(f"{k} {pe[k] / max(v, 1):.1f}" for k, v in ev.items()))
     for k, ms in h.kernel_times():
         print(f"     {k:18s} {ms*1e3:9.1f} us")
     h.close()
