@@ -71,15 +71,15 @@ def many_primitives(n: int = 1024, seed: int = 1234, k: float = 0.1, t: float | 
         period = arng.uniform(2.0, 8.0, size=n)
         centres = centres + amp * np.sin(2.0 * np.pi * t / period)[:, None]
     out = np.zeros(n, dtype=PRIM_DTYPE)
-    for i in range(n):
-        c = centres[i]
-        if i % 3 == 0:
-            out[i] = _prim(SPHERE, FOLD_SMOOTH_MIN, k=k, radius=radius[i], a=c)
-        elif i % 3 == 1:
-            h = 0.5 * seg_len[i] * seg_dir[i]
-            out[i] = _prim(CAPSULE, FOLD_SMOOTH_MIN, k=k, radius=lw[i], a=c - h, b=c + h)
-        else:
-            out[i] = _prim(BOX, FOLD_SMOOTH_MIN, k=k, a=c, b=box[i])
+    i = np.arange(n)
+    sph, cap, box_ = (i % 3 == 0), (i % 3 == 1), (i % 3 == 2)
+    half = 0.5 * seg_len[:, None] * seg_dir
+    out["fold"] = FOLD_SMOOTH_MIN
+    out["k"] = np.float32(k)
+    out["kind"] = np.where(sph, SPHERE, np.where(cap, CAPSULE, BOX))
+    out["radius"] = np.where(sph, radius, np.where(cap, lw, 0.0)).astype(np.float32)
+    out["a"] = np.where(cap[:, None], centres - half, centres).astype(np.float32)
+    out["b"] = np.where(cap[:, None], centres + half, np.where(box_[:, None], box, 0.0)).astype(np.float32)
     return out
 
 
