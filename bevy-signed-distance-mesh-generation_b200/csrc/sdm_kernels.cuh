@@ -448,53 +448,67 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_PROJECT], work);
 }
 
-// Tail phase: one WARP per straggler.  The 13 evaluation points of a Newton step (the iterate and the 12 stencil points
-// of empirical_normal) go to 13 lanes, so a step costs one evaluation's latency instead of thirteen; every lane then
-// forms the same update from the 13 shuffled values (identical arithmetic => identical bits in all lanes).
-__global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ scene, DevState* st, float* __restrict__ upos,
+// Tail phase: one HALF-WARP per straggler.  The 13 evaluation points of a Newton step (the iterate and the 12 stencil
+// points of empirical_normal) go to 13 lanes of the half-warp, so a step costs one evaluation's latency instead of
+// thirteen; every lane then forms the same update from the 13 shuffled values (identical arithmetic => identical bits).
+// Two vertices per warp keep 26 of 32 lanes busy when there are many stragglers (Mandelbulb: ~1 % of all vertices).
+__global__ void __launch_bounds__(128, 8) k_project_tail(const uint4* __restrict__ scene, DevState* st, float* __restrict__ upos,
                                                       const Straggler* __restrict__ stragglers, uint32_t cap_stragglers, MaskGrid grid) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t hl = lane & 15u;            // lane within the half-warp
+    const uint32_t half = lane >> 4;
     const uint32_t n = min(st->n_stragglers, cap_stragglers);
     unsigned long long extra_iters = 0, work = 0;
     while (true) {
-        uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(&st->ticket[TK_TAIL], 1u);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n) break;
-        const Straggler r = stragglers[idx];
+        uint32_t idx0 = 0;
+        if (lane == 0) idx0 = atomicAdd(&st->ticket[TK_TAIL], 2u);
+        idx0 = __shfl_sync(0xffffffffu, idx0, 0);
+        if (idx0 >= n) break;
+        const uint32_t idx = idx0 + half;
+        bool running = idx < n;
+        Straggler r;
+        r.uid = 0; r.it = 0; r.g[0] = r.g[1] = r.g[2] = 0.f; r.s[0] = r.s[1] = r.s[2] = 0.f; r.power = 1; r.lam = 0; r.stop_at = 0; r.pad = 0;
+        if (running) r = stragglers[idx];
         float gx = r.g[0], gy = r.g[1], gz = r.g[2];
         uint32_t it = r.it;
         NewtonCycle cyc;
         cyc.sx = r.s[0]; cyc.sy = r.s[1]; cyc.sz = r.s[2]; cyc.power = r.power; cyc.lam = r.lam; cyc.stop_at = r.stop_at;
-        bool collision = false;
-        while (!collision && it < cyc.stop_at) {
-            tile_mask_from_point(grid, sc, lane == 0, gx, gy, gz);
-            work += (unsigned long long) tile_prims(sc) * 13u;
-            // lane 0: the iterate; lane 1 + 4*axis + s: stencil point s of that axis (same construction as normal_points)
+        running = running && it < cyc.stop_at;
+        while (__any_sync(0xffffffffu, running)) {
+            tile_mask_from_point(grid, sc, running && hl == 0, gx, gy, gz);
+            if (lane == 0) work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, running && hl == 0));
+            else (void) __ballot_sync(0xffffffffu, running && hl == 0);
+            // half-lane 0: the iterate; half-lane 1 + 4*axis + s: stencil point s of that axis (same construction as normal_points)
             float x = gx, y = gy, z = gz;
-            if (lane >= 1 && lane <= 12) {
-                const uint32_t q = lane - 1u, a = q >> 2, sidx = q & 3u;
+            if (hl >= 1 && hl <= 12) {
+                const uint32_t q = hl - 1u, a = q >> 2, sidx = q & 3u;
                 const float o = sidx == 0 ? 2.0f * SDM_NORMAL_EPSILON : (sidx == 1 ? SDM_NORMAL_EPSILON : (sidx == 2 ? -SDM_NORMAL_EPSILON : -2.0f * SDM_NORMAL_EPSILON));
                 x = gx + (a == 0 ? o : 0.0f); y = gy + (a == 1 ? o : 0.0f); z = gz + (a == 2 ? o : 0.0f);
             }
             float fv = 0.0f;
-            if (lane <= 12) fv = eval_scene1(sc, x, y, z);
+            if (running && hl <= 12) fv = eval_scene1(sc, x, y, z);
             float f[13];
 #pragma unroll
-            for (int j = 0; j < 13; j++) f[j] = __shfl_sync(0xffffffffu, fv, j);
-            float nx, ny, nz;
-            normal_from_samples<1>(f, nx, ny, nz);
-            const float sd = f[0];
-            gx -= sd * nx; gy -= sd * ny; gz -= sd * nz;
-            collision = fabsf(sd) <= 0.00001f;
-            it++;
-            if (!collision) cyc.observe(gx, gy, gz, it);
+            for (int j = 0; j < 13; j++) f[j] = __shfl_sync(0xffffffffu, fv, j, 16);
+            if (running) {
+                float nx, ny, nz;
+                normal_from_samples<1>(f, nx, ny, nz);
+                const float sd = f[0];
+                gx -= sd * nx; gy -= sd * ny; gz -= sd * nz;
+                const bool collision = fabsf(sd) <= 0.00001f;
+                it++;
+                if (!collision) cyc.observe(gx, gy, gz, it);
+                running = !collision && it < cyc.stop_at;
+            }
         }
-        if (lane == 0) { upos[3 * (size_t) r.uid] = gx; upos[3 * (size_t) r.uid + 1] = gy; upos[3 * (size_t) r.uid + 2] = gz; }
-        extra_iters += it - r.it;
+        if (idx < n && hl == 0) {
+            upos[3 * (size_t) r.uid] = gx; upos[3 * (size_t) r.uid + 1] = gy; upos[3 * (size_t) r.uid + 2] = gz;
+            extra_iters += it - r.it;
+        }
     }
+    extra_iters += __shfl_xor_sync(0xffffffffu, extra_iters, 16);
     if (lane == 0 && extra_iters) atomicAdd(&st->newton_iters, extra_iters);
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_TAIL], work);
 }
