@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
 // points of empirical_normal) go to 13 lanes of the half-warp, so a step costs one evaluation's latency instead of
 // thirteen; every lane then forms the same update from the 13 shuffled values (identical arithmetic => identical bits).
 // Two vertices per warp keep 26 of 32 lanes busy when there are many stragglers (Mandelbulb: ~1 % of all vertices).
-__global__ void __launch_bounds__(128, 8) k_project_tail(const uint4* __restrict__ scene, DevState* st, float* __restrict__ upos,
+__global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ scene, DevState* st, float* __restrict__ upos,
                                                       const Straggler* __restrict__ stragglers, uint32_t cap_stragglers, MaskGrid grid) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
@@ -476,8 +476,20 @@ __global__ void __launch_bounds__(128, 8) k_project_tail(const uint4* __restrict
         NewtonCycle cyc;
         cyc.sx = r.s[0]; cyc.sy = r.s[1]; cyc.sz = r.s[2]; cyc.power = r.power; cyc.lam = r.lam; cyc.stop_at = r.stop_at;
         running = running && it < cyc.stop_at;
+        // The tile's primitive list is built for a ball of extra radius SLACK around each iterate and kept until an iterate
+        // leaves its ball (or a half finishes): a slow orbit moves ~1e-4 per step, so the list is rebuilt every ~100 steps
+        // instead of every step.  (A larger ball only makes the list a superset: still exact.)
+        const float SLACK = 0.01f;
+        float lcx = gx, lcy = gy, lcz = gz;
+        bool list_valid = false;
         while (__any_sync(0xffffffffu, running)) {
-            tile_mask_from_point(grid, sc, running && hl == 0, gx, gy, gz);
+            const float mvx = gx - lcx, mvy = gy - lcy, mvz = gz - lcz;
+            const bool moved = running && !(mvx * mvx + mvy * mvy + mvz * mvz <= (0.5f * SLACK) * (0.5f * SLACK));   // NaN -> rebuild
+            if (!list_valid || __any_sync(0xffffffffu, moved)) {
+                tile_mask_from_point(grid, sc, running && hl == 0, gx, gy, gz, SLACK);
+                lcx = gx; lcy = gy; lcz = gz;
+                list_valid = true;
+            }
             if (lane == 0) work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, running && hl == 0));
             else (void) __ballot_sync(0xffffffffu, running && hl == 0);
             // half-lane 0: the iterate; half-lane 1 + 4*axis + s: stencil point s of that axis (same construction as normal_points)
