@@ -93,7 +93,7 @@ int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>&
         const H3 a { q.a[0], q.a[1], q.a[2] }, b { q.b[0], q.b[1], q.b[2] };
         DevPrim d;
         memset(&d, 0, sizeof(d));
-        d.kind = q.kind; d.fold = q.fold; d.k = q.k;
+        d.kind = q.kind; d.fold = q.fold; d.k = q.fold == SDM_FOLD_SMOOTH_MIN ? q.k : 0.0f;   // k is only read by smooth folds
         switch (q.kind) {
             case SDM_PRIM_SPHERE:
                 d.v0[0] = a.x; d.v0[1] = a.y; d.v0[2] = a.z; d.s0 = q.radius;
@@ -105,7 +105,7 @@ int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>&
                 dp.push_back(d);
                 break;
             case SDM_PRIM_CAPSULE:
-                dp.push_back(make_capsule(a, b, q.radius, q.fold, q.k));
+                dp.push_back(make_capsule(a, b, q.radius, q.fold, q.fold == SDM_FOLD_SMOOTH_MIN ? q.k : 0.0f));
                 break;
             case SDM_PRIM_BOX_SKELETON: {
                 // The skeleton's own fold is min from FLT_MAX (signed_distance.cu:95,109).  Flattening its 12 edges
