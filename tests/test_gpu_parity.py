@@ -136,3 +136,33 @@ def test_branch_free_sqrt_and_division_are_ieee(handler):
     assert r["sqrt_mismatches"] == 0, r
     assert r["div_mismatches"] == 0, r
     assert r["sqrt_slow_path"] < (1 << 32) * 0.60   # negatives, NaN, denormal-range, huge: sent to sqrtf()
+
+
+def test_empty_scene_and_growth_paths(oracle_mod):
+    """Edge cases of the boundary: a scene with no primitives has no surface (empty list after one refine, empty mesh);
+    a handle whose buffers are too small grows them (the reference always allocates 8n / 5n worst case,
+    src/cuda/mod.rs:125,205) and still returns the same mesh."""
+    h = bsdmg_b200.CudaHandler(0, np.zeros(0, scenes.PRIM_DTYPE))
+    try:
+        h.field_reset(5.0, 16)
+        assert h.field_refine() == 0
+        assert h.field_refine() == 0          # refining an empty field is a no-op (src/cuda/mod.rs:137)
+        m = h.field_to_mesh()
+        assert m.vertex_count == 0 and m.triangle_count == 0
+        m = h.remesh(5.0, 16, 2)
+        assert m.vertex_count == 0 and m.triangle_count == 0
+        # growth: 128^3 level-0 field (2.1 M voxels) exceeds the initial capacity of 2^21 voxels by one refinement
+        scene = scenes.sd_obj()
+        h.set_scene(scene)
+        a = h.remesh(5.0, 128, 2)             # 512^3, grows inside remesh
+        h2 = bsdmg_b200.CudaHandler(0, scene)
+        try:
+            h2.field_reset(5.0, 128)
+            h2.field_refine(); n = h2.field_refine()
+            b = h2.field_to_mesh()
+        finally:
+            h2.close()
+        assert n == 265256                     # SURVEY.md section 8a: active voxels of sd_obj at 512^3
+        assert np.array_equal(a.indices, b.indices) and np.array_equal(bits(a.positions), bits(b.positions))
+    finally:
+        h.close()
