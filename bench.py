@@ -226,6 +226,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         import torch.distributed as dist_mod
 
         dist = dist_mod

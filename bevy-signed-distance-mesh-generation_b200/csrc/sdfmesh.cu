@@ -187,8 +187,15 @@ struct SdmHandle {
     // mesh intermediates
     uint32_t cap_tris = 0, cap_uniq = 0, table_entries = 0;
     DevBuf<uint8_t> cases;
-    DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix, out_idx;
-    DevBuf<float> ustart, upos, unrm, out_pos, out_nrm;
+    DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
+    DevBuf<float> ustart, upos, unrm;
+    // Mesh outputs are double-buffered: while one mesh is being copied to the host on copy_stream (sdm_mesh_download_async)
+    // the next remesh writes the other set.
+    DevBuf<uint32_t> out_idx[2];
+    DevBuf<float> out_pos[2], out_nrm[2];
+    int out_sel = 0;                     // set the NEXT weld writes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_mesh_done[2] = { nullptr, nullptr }, ev_copy_done[2] = { nullptr, nullptr };
     DevBuf<uint4> table1, table2;
     DevBuf<uint64_t> tiles, tiles2;
     DevBuf<Straggler> stragglers;
@@ -311,6 +318,7 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
 
 int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     if (cap_vox <= h->cap_vox) return SDM_OK;
+    if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));   // no download may be reading a buffer that is about to move
     // copy-preserving growth of the current list is not needed: callers re-create the field after growing
     h->cap_vox = cap_vox;
     h->cap_tris = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 3, 0x3FFFFFFFull);   // < 2^32 / 3 slots
@@ -321,7 +329,7 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     CK(h->tri_off.reserve(cap_vox));
     CK(h->slot_ref.reserve((size_t) h->cap_tris * 3));
     CK(h->tri_uid.reserve((size_t) h->cap_tris * 3));
-    CK(h->out_idx.reserve((size_t) h->cap_tris * 3));
+    for (int b = 0; b < 2; b++) CK(h->out_idx[b].reserve((size_t) h->cap_tris * 3));
     CK(h->first_bits.reserve(((size_t) h->cap_tris * 3 + 31) / 32 + 32));
     CK(h->first_prefix.reserve(((size_t) h->cap_tris * 3 + 31) / 32 + 32));
     CK(h->tri_valid_bits.reserve(((size_t) h->cap_tris + 31) / 32 + 32));
@@ -331,8 +339,7 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     CK(h->ustart.reserve((size_t) h->cap_uniq * 3));
     CK(h->upos.reserve((size_t) h->cap_uniq * 3));
     CK(h->unrm.reserve((size_t) h->cap_uniq * 3));
-    CK(h->out_pos.reserve((size_t) h->cap_uniq * 3));
-    CK(h->out_nrm.reserve((size_t) h->cap_uniq * 3));
+    for (int b = 0; b < 2; b++) { CK(h->out_pos[b].reserve((size_t) h->cap_uniq * 3)); CK(h->out_nrm[b].reserve((size_t) h->cap_uniq * 3)); }
     CK(h->table1.reserve(h->table_entries));
     CK(h->table2.reserve(h->table_entries));
     const size_t max_tiles = std::max<size_t>(((size_t) h->cap_tris * 3 / 32 + 31) / 32, (size_t) cap_vox / 32) + 64;
@@ -457,6 +464,8 @@ int enqueue_mesh_local(SdmHandle* h) {
 // the reference-order weld over (upos, unrm, tri_uid, first_slot, tri_valid_bits) and the counters in DevState
 int enqueue_weld(SdmHandle* h) {
     cudaStream_t s = h->stream;
+    const int b = h->out_sel;
+    CK(cudaStreamWaitEvent(s, h->ev_copy_done[b], 0));   // the download of the mesh that used this set two remeshes ago
     k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, h->table_entries, h->wref.p, h->cap_uniq);
     mark(h, "k_weld_insert");
     k_weld_mark<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->cap_uniq);
@@ -465,11 +474,12 @@ int enqueue_weld(SdmHandle* h) {
     k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_valid_bits.p, h->tri_prefix.p, 1, next_epoch(h), h->tiles.p);
     mark(h, "k_bitscan_x2");
     k_emit_vertices<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
-                                                h->upos.p, h->unrm.p, h->out_pos.p, h->out_nrm.p, h->cap_uniq);
+                                                h->upos.p, h->unrm.p, h->out_pos[b].p, h->out_nrm[b].p, h->cap_uniq);
     mark(h, "k_emit_vertices");
     k_emit_indices<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
-                                               h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx.p);
+                                               h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx[b].p);
     mark(h, "k_emit_indices");
+    CK(cudaEventRecord(h->ev_mesh_done[b], s));
     h->stats.kernel_launches += 6;
     CK(cudaGetLastError());
     return SDM_OK;
@@ -506,13 +516,15 @@ void fill_stats(SdmHandle* h, bool meshed) {
 }
 
 void mesh_view(SdmHandle* h, SdmMesh* m) {
-    m->positions = h->out_pos.p;
-    m->normals = h->out_nrm.p;
-    m->indices = h->out_idx.p;
+    const int b = h->out_sel;          // the set the weld that just finished wrote
+    m->positions = h->out_pos[b].p;
+    m->normals = h->out_nrm[b].p;
+    m->indices = h->out_idx[b].p;
+    h->out_sel ^= 1;
     m->vertex_count = h->host_state->n_verts_out;
     m->triangle_count = h->host_state->n_tris_out;
     m->on_device = 1;
-    m->reserved = 0;
+    m->reserved = b;
 }
 
 int check_params(const SdmParams& p) {
@@ -590,6 +602,8 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         h->num_sms = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "stream"); break; }
         cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+        for (int b = 0; b < 2; b++) { cudaEventCreateWithFlags(&h->ev_mesh_done[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_copy_done[b], cudaEventDisableTiming); }
         if (cudaMallocHost(&h->host_state, sizeof(DevState)) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMallocHost"); break; }
         memset(h->host_state, 0, sizeof(DevState));
         if (cudaMallocHost(&h->host_range, 16) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMallocHost"); break; }
@@ -616,11 +630,14 @@ void sdm_destroy(SdmHandle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int b = 0; b < 2; b++) { if (h->ev_mesh_done[b]) cudaEventDestroy(h->ev_mesh_done[b]); if (h->ev_copy_done[b]) cudaEventDestroy(h->ev_copy_done[b]); }
     h->masks_fine.release(); h->masks_coarse.release();
     h->scene.release(); h->vox[0].release(); h->vox[1].release(); h->cases.release(); h->tri_off.release(); h->slot_ref.release();
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
-    h->tri_valid_bits.release(); h->tri_prefix.release(); h->out_idx.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
-    h->out_pos.release(); h->out_nrm.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
+    h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
+    for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
+    h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     h->shard_range.release();
@@ -908,6 +925,28 @@ int sdm_mesh_download(SdmHandle* h, const SdmMesh* m, float* positions, float* n
     if (m->vertex_count && normals) CK(cudaMemcpyAsync(normals, m->normals, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, h->stream));
     if (m->triangle_count && indices) CK(cudaMemcpyAsync(indices, m->indices, (size_t) m->triangle_count * 12, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return SDM_OK;
+}
+
+// Asynchronous hand-off to the host: copies on the handle's copy stream, ordered after the weld that produced `m`; the next
+// sdm_remesh may be issued immediately (it writes the other output set).  Host memory should be pinned.
+int sdm_mesh_download_async(SdmHandle* h, const SdmMesh* m, float* positions, float* normals, uint32_t* indices) {
+    if (!h || !m) return fail(SDM_ERR_INVALID, "null argument");
+    if (!m->on_device || m->reserved < 0 || m->reserved > 1) return fail(SDM_ERR_INVALID, "not a device mesh of this library");
+    CK(cudaSetDevice(h->device));
+    const int b = m->reserved;
+    cudaStream_t cs = h->copy_stream;
+    CK(cudaStreamWaitEvent(cs, h->ev_mesh_done[b], 0));
+    if (m->vertex_count && positions) CK(cudaMemcpyAsync(positions, m->positions, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, cs));
+    if (m->vertex_count && normals) CK(cudaMemcpyAsync(normals, m->normals, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, cs));
+    if (m->triangle_count && indices) CK(cudaMemcpyAsync(indices, m->indices, (size_t) m->triangle_count * 12, cudaMemcpyDeviceToHost, cs));
+    CK(cudaEventRecord(h->ev_copy_done[b], cs));
+    return SDM_OK;
+}
+int sdm_mesh_download_wait(SdmHandle* h) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->copy_stream));
     return SDM_OK;
 }
 

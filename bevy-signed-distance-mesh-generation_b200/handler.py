@@ -80,7 +80,7 @@ ABI_SYMBOLS = [
     "sdm_voxel_field_to_mesh", "sdm_mesh_free", "sdm_field_reset", "sdm_field_upload", "sdm_field_refine", "sdm_field_count",
     "sdm_field_download", "sdm_field_cases", "sdm_field_to_mesh", "sdm_remesh", "sdm_mesh_download", "sdm_field_triangle_soup",
     "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
-    "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math",
+    "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
 
 
@@ -337,6 +337,14 @@ class CudaHandler:
         out = (ctypes.c_ulonglong * 4)()
         self._check(self._lib.sdm_selftest_math(self._h, ctypes.c_ulonglong(div_samples), out))
         return dict(sqrt_mismatches=int(out[0]), sqrt_slow_path=int(out[1]), div_mismatches=int(out[2]), div_slow_path=int(out[3]))
+
+    def download_into_async(self, m, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:
+        """sdm_mesh_download_async: the copy overlaps the next remesh (outputs are double-buffered in the handle)."""
+        self._check(self._lib.sdm_mesh_download_async(self._h, ctypes.byref(m), ctypes.c_void_p(positions_ptr), ctypes.c_void_p(normals_ptr),
+                                                      ctypes.c_void_p(indices_ptr)))
+
+    def download_wait(self) -> None:
+        self._check(self._lib.sdm_mesh_download_wait(self._h))
 
     def set_profiling(self, enabled: bool) -> None:
         self._check(self._lib.sdm_set_profiling(self._h, ctypes.c_int(1 if enabled else 0)))

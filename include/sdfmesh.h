@@ -97,7 +97,7 @@ typedef struct SdmMesh {
     uint32_t vertex_count;
     uint32_t triangle_count;
     int32_t on_device;             /* 1: pointers are device memory owned by the handle */
-    int32_t reserved;
+    int32_t reserved;              /* device meshes: which of the handle's two output sets holds it */
 } SdmMesh;
 
 typedef struct SdmHandle SdmHandle;
@@ -151,6 +151,12 @@ int sdm_field_to_mesh(SdmHandle* h, SdmMesh* out_mesh);
 int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh);
 /* Copies a device-resident mesh into caller-provided host arrays (sizes from the SdmMesh counts). */
 int sdm_mesh_download(SdmHandle* h, const SdmMesh* device_mesh, float* positions, float* normals, uint32_t* indices);
+/* Streaming hand-off: the copies run on a second stream, ordered after the weld that produced `device_mesh`; mesh outputs
+ * are double-buffered inside the handle, so the next sdm_remesh can be issued right away and overlaps the download.  At
+ * most one download per output set may be in flight (i.e. call sdm_mesh_download_async once per remesh); host memory
+ * should be pinned.  sdm_mesh_download_wait blocks until all issued downloads have landed. */
+int sdm_mesh_download_async(SdmHandle* h, const SdmMesh* device_mesh, float* positions, float* normals, uint32_t* indices);
+int sdm_mesh_download_wait(SdmHandle* h);
 /* The reference's raw output format: 5 Triangle slots per voxel, NaN-padded
  * (compute_mesh_generation.cu:64-120), to host (capacity in triangles, >= 5 * voxel_count). */
 int sdm_field_triangle_soup(SdmHandle* h, SdmTriangle* out_triangles, uint32_t capacity);

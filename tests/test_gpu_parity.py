@@ -166,3 +166,25 @@ def test_empty_scene_and_growth_paths(oracle_mod):
         assert np.array_equal(a.indices, b.indices) and np.array_equal(bits(a.positions), bits(b.positions))
     finally:
         h.close()
+
+
+def test_async_download_overlaps_and_matches(handler):
+    """sdm_mesh_download_async: outputs are double-buffered, so a mesh being copied must survive the next remesh."""
+    import torch
+
+    handler.set_scene(scenes.sd_obj())
+    want = {lv: handler.remesh(5.0, 32, lv) for lv in (1, 2, 3)}
+    bufs = {}
+    for lv in (1, 2, 3, 2, 1):
+        m = handler.remesh(5.0, 32, lv, download=False)
+        nv, nt = int(m.vertex_count), int(m.triangle_count)
+        pos = torch.empty((nv, 3), dtype=torch.float32).pin_memory()
+        nrm = torch.empty((nv, 3), dtype=torch.float32).pin_memory()
+        idx = torch.empty((nt, 3), dtype=torch.int32).pin_memory()
+        handler.download_into_async(m, pos.data_ptr(), nrm.data_ptr(), idx.data_ptr())
+        bufs.setdefault(lv, []).append((pos, nrm, idx))
+    handler.download_wait()
+    for lv, lst in bufs.items():
+        for pos, nrm, idx in lst:
+            assert np.array_equal(idx.numpy().view(np.uint32), want[lv].indices)
+            assert np.array_equal(bits(pos.numpy()), bits(want[lv].positions)) and np.array_equal(bits(nrm.numpy()), bits(want[lv].normals))
