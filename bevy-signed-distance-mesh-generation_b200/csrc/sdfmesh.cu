@@ -571,16 +571,21 @@ int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count) {
     int rc = compile_scene(prims, count, blob, &mb);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the previous table may still be in use
     CK(h->scene.reserve(blob.size()));
     CK(cudaMemcpyAsync(h->scene.p, blob.data(), blob.size() * 16, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // `blob` is a local
+    const uint32_t old_bytes = h->scene_bytes, old_nprims = h->scene_nprims;
+    const bool old_capable = h->mask_capable;
     h->scene_bytes = (uint32_t) (blob.size() * 16);
     h->scene_nprims = reinterpret_cast<const SceneHeader*>(blob.data())->nprims;
     // culling pays off once the table is long; it needs 1-Lipschitz primitives (not the Mandelbulb estimator)
     h->mask_capable = !mb && h->scene_nprims > 24;
     h->grid.enabled = 0;   // masks depend on the scene: rebuilt on the next remesh
     h->mesh_valid = false;
+    // shared-memory sizes / persistent grid sizes only depend on these three: an animated scene (same table shape every
+    // frame) does not pay for the occupancy queries again
+    if (h->g_refine && old_bytes == h->scene_bytes && old_nprims == h->scene_nprims && old_capable == h->mask_capable) return SDM_OK;
     return configure_kernels(h);
 }
 

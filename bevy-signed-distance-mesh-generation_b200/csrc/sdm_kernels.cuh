@@ -922,11 +922,18 @@ __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ s
             prow = parent_masks + ((size_t) (((ix / f) * parent_G + iy / f) * parent_G + iz / f)) * g.W;
         }
         float carry = inf;
-        for (uint32_t w = 0; w < g.W; w++) {
-            const uint32_t pm = prow ? prow[w] : 0xFFFFFFFFu;
-            uint32_t word = 0;
-            if (pm) {
-                const uint32_t j = (w << 5) + lane;
+        // lane w keeps parent word w and result word w: one coalesced load and one coalesced store per cell (32 words per
+        // pass), and only the non-empty parent words are visited
+        for (uint32_t w0 = 0; w0 < g.W; w0 += 32u) {
+            const uint32_t wl = w0 + lane;
+            const uint32_t pmw = wl < g.W ? (prow ? prow[wl] : 0xFFFFFFFFu) : 0u;
+            uint32_t myword = 0;
+            uint32_t nz = __ballot_sync(0xffffffffu, pmw != 0u);
+            while (nz) {
+                const uint32_t wi = (uint32_t) __ffs((int) nz) - 1u;
+                nz &= nz - 1u;
+                const uint32_t pm = __shfl_sync(0xffffffffu, pmw, wi);
+                const uint32_t j = ((w0 + wi) << 5) + lane;
                 const bool active = ((pm >> lane) & 1u) && j < sc.nprims;
                 float d = inf, kk = 0.0f;
                 if (active) {
@@ -946,10 +953,11 @@ __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ s
                 if (lane == 0) excl = inf;
                 const float U = fminf(carry, excl);
                 const bool keep = active && !(d - rho >= U + kk + 1e-4f);   // NaN distance: keep
-                word = __ballot_sync(0xffffffffu, keep);
+                const uint32_t word = __ballot_sync(0xffffffffu, keep);
+                if (lane == wi) myword = word;
                 carry = fminf(carry, total);
             }
-            if (lane == 0) out_masks[(size_t) cell * g.W + w] = word;
+            if (wl < g.W) out_masks[(size_t) cell * g.W + wl] = myword;
         }
     }
 }
