@@ -447,7 +447,8 @@ int enqueue_mesh_local(SdmHandle* h) {
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
-    k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid);
+    k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid,
+                                                 512u);   // vertex chunk per warp (B200 sweep: 256..768 within 3 %)
     mark(h, "k_project");
     k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid);
     mark(h, "k_project_tail");

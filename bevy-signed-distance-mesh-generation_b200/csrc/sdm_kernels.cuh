@@ -372,7 +372,7 @@ struct Straggler { uint32_t uid, it; float g[3]; float s[3]; uint32_t power, lam
 
 __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart,
                                                  float* __restrict__ upos, uint32_t cap_uniq, Straggler* __restrict__ stragglers,
-                                                 uint32_t cap_stragglers, MaskGrid grid) {
+                                                 uint32_t cap_stragglers, MaskGrid grid, uint32_t max_chunk) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) k_project(const uint4* __restrict__ scene
     // per warp at a time: the lanes of a warp then work in one neighbourhood, which keeps the tile's primitive list short.
     // chunk size: large enough for coherence, small enough that every warp gets >= ~4 chunks (load balance)
     const uint32_t warps_in_grid = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t CHUNK = sc.wmask ? min(256u, max(32u, ((n / (warps_in_grid * 4u) + 31u) >> 5) << 5)) : 32u;   // coherence only matters when culling
+    const uint32_t CHUNK = sc.wmask ? min(max_chunk, max(32u, ((n / (warps_in_grid * 4u) + 31u) >> 5) << 5)) : 32u;   // coherence only matters when culling
     uint32_t chunk_next = 0, chunk_end = 0;
     bool drained = false;
     while (true) {

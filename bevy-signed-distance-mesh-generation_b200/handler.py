@@ -133,6 +133,31 @@ class Mesh:
     def vertex_count(self) -> int:
         return int(self.positions.shape[0])
 
+    def save_obj(self, path) -> None:
+        """Writes the mesh the way the reference does when the `Mesh` stage is advanced (src/renderer/mod.rs:204,
+        `obj.save("generated_mesh.obj")` on the ObjData built at src/cuda/mod.rs:303-326): all `v` lines, the single
+        `vt 0 0`, all `vn` lines, object and group "default", and one `f a/1/a b/1/b c/1/c` per triangle (1-based;
+        position index == normal index, texture index 0 -> 1).  Floats use Rust's `{}` formatting of f32: shortest
+        digits that round-trip, positional notation.  (The `obj` crate 0.10.2 is not vendored in the reference tree,
+        so the line layout is restated from its documented format - unpinned.)"""
+        f32 = lambda x: np.format_float_positional(np.float32(x), unique=True, trim="-") if np.isfinite(x) else ("NaN" if np.isnan(x) else ("inf" if x > 0 else "-inf"))
+        with open(path, "w") as out:
+            for p in self.positions:
+                out.write(f"v {f32(p[0])} {f32(p[1])} {f32(p[2])}\n")
+            out.write("vt 0 0\n")
+            for n in self.normals:
+                out.write(f"vn {f32(n[0])} {f32(n[1])} {f32(n[2])}\n")
+            out.write("o default\ng default\n")
+            for t in self.indices:
+                a, b, c = int(t[0]) + 1, int(t[1]) + 1, int(t[2]) + 1
+                out.write(f"f {a}/1/{a} {b}/1/{b} {c}/1/{c}\n")
+
+    def bevy_attributes(self) -> dict:
+        """The three buffers `obj_to_bevy_mesh` hands to Bevy (src/renderer/mod.rs:110-128): ATTRIBUTE_POSITION and
+        ATTRIBUTE_NORMAL as Float32x3 arrays, Indices::U32 as the flat triangle list."""
+        return {"ATTRIBUTE_POSITION": np.ascontiguousarray(self.positions, np.float32), "ATTRIBUTE_NORMAL": np.ascontiguousarray(self.normals, np.float32),
+                "Indices::U32": np.ascontiguousarray(self.indices, np.uint32).reshape(-1)}
+
     @property
     def triangle_count(self) -> int:
         return int(self.indices.shape[0])

@@ -67,3 +67,16 @@ def test_no_cpu_fallback():
     with pytest.raises(bsdmg_b200.SdfMeshError) as e:
         bsdmg_b200.CudaHandler(0)
     assert e.value.code == 3   # SDM_ERR_NO_DEVICE
+
+
+def test_obj_writer_layout(tmp_path):
+    """Mesh.save_obj: the layout the reference's `obj.save` produces for its ObjData (src/cuda/mod.rs:303-326)."""
+    m = bsdmg_b200.Mesh(np.float32([[0, 0.5, -1.25], [1, 1e-5, 2], [3, 4, 5]]), np.float32([[0, 0, 1], [0, 1, 0], [1, 0, 0]]), np.uint32([[0, 1, 2]]))
+    p = tmp_path / "generated_mesh.obj"
+    m.save_obj(p)
+    lines = p.read_text().splitlines()
+    assert lines[0] == "v 0 0.5 -1.25" and lines[1] == "v 1 0.00001 2"
+    assert lines[3] == "vt 0 0" and lines[4] == "vn 0 0 1"
+    assert lines[7:9] == ["o default", "g default"] and lines[9] == "f 1/1/1 2/1/2 3/1/3"
+    a = m.bevy_attributes()
+    assert a["Indices::U32"].tolist() == [0, 1, 2] and a["ATTRIBUTE_POSITION"].shape == (3, 3)
