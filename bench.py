@@ -332,6 +332,8 @@ def main():
             "kernel_ms": {k: round(v, 5) for k, v in kavg.items()},
             "roofline": roofline, "roofline_hbm": roofline_hbm,
         }
+        if world > 1:
+            line["rank0_phase_ms"] = dict(zip(("local_shard", "count_allgather", "gather", "weld"), getattr(runner, "last_phases", [])))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sampled_remesh(scene_name, scene, bb, init, levels, res)
         print(json.dumps(line), flush=True)

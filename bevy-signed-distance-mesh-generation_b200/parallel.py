@@ -79,12 +79,15 @@ class ShardedRemesher:
 
         dist, h = self.dist, self.h
         dev = torch.device("cuda", torch.cuda.current_device())
+        tm = [time.perf_counter()]
         info = h.shard_remesh(self.bb, self.init, self.levels, self.split_level, self.rank, self.world)
+        tm.append(time.perf_counter())
         gpu_ms = h.stats()["last_gpu_ms"]
         mine = torch.tensor([info["unique_vertices"], info["raw_triangles"]], dtype=torch.int64, device=dev)
         allc = torch.empty((self.world, 2), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allc, mine)
         counts = [(int(a), int(b)) for a, b in allc.cpu().tolist()]
+        tm.append(time.perf_counter())
         v_off, t_off, (V, T) = plan_offsets(counts)
         ops = []
         if self.rank == 0:
@@ -110,6 +113,7 @@ class ShardedRemesher:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         torch.cuda.current_stream().synchronize()
+        tm.append(time.perf_counter())
         out = {"triangles": 0, "vertices": 0}
         if self.rank == 0:
             m = h.shard_weld(V, T)
@@ -117,6 +121,9 @@ class ShardedRemesher:
             self.mesh = m
             out = {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
         self.last_gpu_ms = gpu_ms
+        tm.append(time.perf_counter())
+        # host-side phase times of the last step (ms): local shard, count all-gather, gather, weld
+        self.last_phases = [round((b - a) * 1e3, 3) for a, b in zip(tm[:-1], tm[1:])]
         return out
 
     def step(self):
