@@ -261,7 +261,9 @@ void prof_end(SdmHandle* h) {   // after the stream has been synchronised
 }
 
 int configure_kernels(SdmHandle* h) {
-    if (smem_for(h, 256, true) > 200 * 1024) return fail(SDM_ERR_INVALID, "scene table does not fit in shared memory (max ~3000 primitives)");
+    if (!h->mask_capable && smem_for(h, 256, true) > 200 * 1024)
+        return fail(SDM_ERR_INVALID, "an un-culled scene table must fit in shared memory (max ~3000 primitives)");
+    if (h->scene_nprims > 65535) return fail(SDM_ERR_INVALID, "too many primitives (tile lists hold 16-bit indices)");
     struct K { const void* f; int threads; int* grid; };
     const K ks[] = {
         { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify_edges, 256, &h->g_classify },
@@ -278,7 +280,6 @@ int configure_kernels(SdmHandle* h) {
     }
     for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project })
         CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 128), 1024)));
-    CK(cudaFuncSetAttribute((const void*) k_build_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 256, true), 1024)));
     h->g_light = h->num_sms * 8;
     return SDM_OK;
 }
@@ -303,9 +304,8 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     // radius = circumsphere of the cell cube (x1.0001) + the empirical_normal stencil reach (2e-3, signed_distance.cu:179)
     //          + slop for the inward-nudged box probes and the domain-face tolerance (2e-3 cell) + 1e-4
     auto rho = [](float cell) { return cell * 0.8660254f * 1.0001f + 0.0021f + 2e-3f * cell + 1e-4f; };
-    const size_t smem = smem_for(h, 256, true);
-    k_build_masks<<<h->num_sms * 4, 256, smem, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell));
-    k_build_masks<<<h->num_sms * 8, 256, smem, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell));
+    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell));
+    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell));
     mark(h, "k_build_masks_x2");
     h->stats.kernel_launches += 2;
     CK(cudaGetLastError());

@@ -907,8 +907,12 @@ __global__ void __launch_bounds__(256) k_selftest_math(unsigned long long* __res
 // a primitive outside the parent's mask is already proven droppable on the parent's sphere, which contains the child's.
 __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ scene, uint32_t* __restrict__ out_masks, MaskGrid g,
                                                      const uint32_t* __restrict__ parent_masks, uint32_t parent_G, float rho) {
-    extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene(scene, smem);
+    // the table is read through L1 (each lane reads a different record: from shared memory that would be a 16-way bank
+    // conflict, and staging 64 KB per block would cap occupancy)
+    const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(scene);
+    SceneView sc;
+    sc.runs = nullptr; sc.nruns = 0; sc.nprims = hdr.nprims; sc.wmask = nullptr; sc.W = 0; sc.tcand = nullptr; sc.tlist = nullptr; sc.tcount = nullptr;
+    sc.prims = reinterpret_cast<const DevPrim*>(scene + 1 + hdr.nruns);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t ncells = g.G * g.G * g.G;
