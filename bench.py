@@ -291,7 +291,7 @@ def main():
         # dominant SDF kernel: achieved = (primitive, point) distance evaluations it actually folded (device counters, after
         # culling) x algorithmic FP32 ops per such evaluation (scene average) / its CUDA-event time
         pe = st["prim_evals"]
-        stage_of = {"k_refine": "refine", "k_classify_edges": "classify", "k_project": "project", "k_vertex_normals": "normals", "k_orient": "orient"}
+        stage_of = {"k_refine": "refine", "k_cases+k_tri_offsets": "classify", "k_project": "project", "k_vertex_normals": "normals", "k_orient": "orient"}
         cand = {k: v for k, v in kavg.items() if k in stage_of}
         top = max(cand, key=cand.get)
         nprims_compiled = sum(12 if int(p["kind"]) == 3 else 1 for p in scene)

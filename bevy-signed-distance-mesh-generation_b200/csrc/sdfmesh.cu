@@ -150,7 +150,9 @@ int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>&
     }
     const size_t bytes = 16 + runs.size() * sizeof(DevRun) + dp.size() * sizeof(DevPrim);
     blob.assign(bytes / 16, make_uint4(0, 0, 0, 0));
-    SceneHeader hdr { (uint32_t) dp.size(), (uint32_t) runs.size(), (uint32_t) bytes, 0 };
+    float kmax = 0.0f;
+    for (const DevPrim& q : dp) if (q.fold == SDM_FOLD_SMOOTH_MIN) kmax = std::max(kmax, q.k);
+    SceneHeader hdr { (uint32_t) dp.size(), (uint32_t) runs.size(), (uint32_t) bytes, kmax };
     memcpy(blob.data(), &hdr, 16);
     if (!runs.empty()) memcpy(blob.data() + 1, runs.data(), runs.size() * sizeof(DevRun));
     if (!dp.empty()) memcpy(blob.data() + 1 + runs.size(), dp.data(), dp.size() * sizeof(DevPrim));
@@ -187,6 +189,7 @@ struct SdmHandle {
     // mesh intermediates
     uint32_t cap_tris = 0, cap_uniq = 0, table_entries = 0;
     DevBuf<uint8_t> cases;
+    DevBuf<uint16_t> won;              // per voxel: edges whose vertex-table entry this voxel created
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
     DevBuf<float> ustart, upos, unrm;
     // Mesh outputs are double-buffered: while one mesh is being copied to the host on copy_stream (sdm_mesh_download_async)
@@ -211,7 +214,7 @@ struct SdmHandle {
     bool mesh_valid = false;
 
     // persistent grid sizes
-    int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0;
+    int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0, g_edges = 0;
 
     SdmStats stats {};
 
@@ -266,7 +269,7 @@ int configure_kernels(SdmHandle* h) {
     if (h->scene_nprims > 65535) return fail(SDM_ERR_INVALID, "too many primitives (tile lists hold 16-bit indices)");
     struct K { const void* f; int threads; int* grid; };
     const K ks[] = {
-        { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_classify_edges, 256, &h->g_classify },
+        { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_cases, 256, &h->g_classify },
         { (const void*) k_project, 128, &h->g_project }, { (const void*) k_vertex_normals, 128, &h->g_normals },
         { (const void*) k_orient, 128, &h->g_orient },   { (const void*) k_project_tail, 128, &h->g_tail },
     };
@@ -281,6 +284,11 @@ int configure_kernels(SdmHandle* h) {
     for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project })
         CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 128), 1024)));
     h->g_light = h->num_sms * 8;
+    {   // static-shared-memory kernels of the classification stage
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edges, 256, 0));
+        h->g_edges = std::max(per_sm, 1) * h->num_sms;
+    }
     return SDM_OK;
 }
 
@@ -325,7 +333,8 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     h->cap_uniq = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 2, 0x7FFFFFFFull);
     h->table_entries = pow2_at_least((uint64_t) h->cap_uniq * 2);
     for (int i = 0; i < 2; i++) CK(h->vox[i].reserve((size_t) cap_vox * 3));
-    CK(h->cases.reserve(cap_vox));
+    CK(h->cases.reserve((size_t) cap_vox + 4));
+    CK(h->won.reserve(cap_vox));
     CK(h->tri_off.reserve(cap_vox));
     CK(h->slot_ref.reserve((size_t) h->cap_tris * 3));
     CK(h->tri_uid.reserve((size_t) h->cap_tris * 3));
@@ -439,11 +448,15 @@ int enqueue_mesh_local(SdmHandle* h) {
     // an overflow is detected (ERR_HASH_FULL) and retried with the full table
     CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table1_entries * 16, s));
     mark(h, "clears");
-    const uint32_t e_tri = next_epoch(h), e_uid = next_epoch(h);
-    k_classify_edges<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, e_tri, e_uid, h->tiles.p, h->tiles2.p, h->cases.p,
-                                                       h->tri_off.p, h->cap_tris, h->table1.p, h->table1_entries - 1, h->ustart.p, h->cap_uniq,
-                                                       h->slot_ref.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? 1 : 0);
-    mark(h, "k_classify_edges");
+    k_cases<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, h->cases.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? 1 : 0);
+    k_tri_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->cases.p, h->tri_off.p, next_epoch(h), h->tiles.p, h->cap_tris);
+    mark(h, "k_cases+k_tri_offsets");
+    k_edges<<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->won.p, sx, sy, sz);
+    mark(h, "k_edges");
+    k_assign_uids<<<h->g_light, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->won.p, h->table1.p, h->slot_ref.p, h->ustart.p, h->cap_uniq,
+                                            next_epoch(h), h->tiles2.p, sx, sy, sz);
+    mark(h, "k_assign_uids");
+    h->stats.kernel_launches += 3;
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
@@ -538,7 +551,7 @@ uint32_t grown(uint32_t cap) { return (uint32_t) std::min<uint64_t>((uint64_t) c
 
 // after a successful mesh: size the vertex table of the next mesh from this one
 void adapt_table1(SdmHandle* h) {
-    const uint32_t want = pow2_at_least(std::max<uint64_t>((uint64_t) h->host_state->n_uniq * 5 / 2, 1u << 16));
+    const uint32_t want = pow2_at_least(std::max<uint64_t>((uint64_t) h->host_state->n_uniq * 7 / 4, 1u << 16));
     h->table1_entries = std::min(want, h->table_entries);
 }
 // the adaptive vertex table was too small (and nothing else overflowed): retry with the full table, same capacities
@@ -643,7 +656,7 @@ void sdm_destroy(SdmHandle* h) {
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
-    h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
+    h->won.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     h->shard_range.release();

@@ -26,7 +26,7 @@ namespace sdm {
 
 namespace cg = cooperative_groups;
 
-enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_COUNT = 24 };
+enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_COUNT = 24 };
 enum ErrFlag : uint32_t {
     ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u
 };
@@ -211,133 +211,226 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
     }
 }
 
-// Marching-cubes classification and edge vertices of one tile of 32 voxels (one lane = one voxel):
-//   * 8 corner evaluations in registers -> cube_index (marching_cubes.cu:19-23), triangle count from the table
-//   * every edge the case uses gets its mid-point mix(a, b, 0.5f) (marching_cubes.cu:13-16), de-duplicated across
-//     voxels by the exact bit pattern of the mid-point in a 128-bit-CAS hash table: an identical start point gives an
-//     identical projection, normal and weld key, so it is projected once instead of once per incident triangle
-//     (~6x); mid-points that differ in any bit stay separate and are merged - if at all - by the reference's quantised
-//     weld later, exactly as the reference would
-//   * two look-backs give the tile's triangle offset and the ids of the vertices it created; ids are handed out in
-//     list order, so consecutive ids are spatial neighbours (this keeps the later per-vertex kernels' primitive
-//     masks small and their loads coalesced)
-//   * slot_ref[3*triangle + corner] = hash entry of that corner's vertex.
-__global__ void __launch_bounds__(256) k_classify_edges(const uint4* __restrict__ scene, const float* __restrict__ vox, DevState* st,
-                                                        int level, uint32_t epoch_tri, uint32_t epoch_uid, uint64_t* tiles_tri, uint64_t* tiles_uid,
-                                                        uint8_t* __restrict__ cases, uint32_t* __restrict__ tri_off, uint32_t cap_tris,
-                                                        uint4* table, uint32_t table_mask, float* __restrict__ ustart, uint32_t cap_uniq,
-                                                        uint32_t* __restrict__ slot_ref, float sx, float sy, float sz, MaskGrid grid,
-                                                        int have_cases) {
+// ---- classification and edge vertices -------------------------------------------------------------------------
+// The stage is split into four small kernels so that the hash phase (latency-bound) runs without any barrier or look-back:
+//   k_cases        8 corner evaluations -> cube_index (marching_cubes.cu:19-23); skipped on the device when the last
+//                  k_refine already wrote the case indices from its lattice signs
+//   k_tri_offsets  triangle count per voxel from the case table, exclusive scan in list order -> tri_off, n_tris_raw
+//   k_edges        every edge the case uses gets its mid-point mix(a, b, 0.5f) (marching_cubes.cu:13-16), de-duplicated
+//                  across voxels by the exact bit pattern of the mid-point in a 128-bit-CAS hash table: an identical
+//                  start point gives an identical projection, normal and weld key, so it is projected once instead of
+//                  once per incident triangle (~6x); mid-points that differ in any bit stay separate and are merged - if
+//                  at all - by the reference's quantised weld later, exactly as the reference would.
+//                  slot_ref[3*triangle + corner] = hash entry of that corner's vertex; won[v] = edges whose entry this
+//                  voxel created
+//   k_assign_uids  scan of popc(won) in list order -> vertex ids (consecutive ids are spatial neighbours: this keeps the
+//                  later per-vertex kernels' primitive lists short and their loads coalesced); writes the start points
+//                  and the id into the winner's hash entry.
+__device__ __forceinline__ void mc_edge_corners(int e, int& c0, int& c1) {   // MC_EDGE_TABLE (marching_cubes_constants.cu:3-16)
+    c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
+    c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
+}
+// mid-point of edge e of the voxel at (bx,by,bz): mix(a, b, 0.5f) = a * (1.0f - 0.5f) + b * 0.5f with the corners of
+// compute_mesh_generation.cu:77-86
+__device__ __forceinline__ void edge_midpoint(float bx, float by, float bz, float sx, float sy, float sz, int e, float& mx, float& my, float& mz) {
+    int c0, c1;
+    mc_edge_corners(e, c0, c1);
+    float ax, ay, az, cx, cy, cz;
+    voxel_corner(bx, by, bz, sx, sy, sz, c0, ax, ay, az);
+    voxel_corner(bx, by, bz, sx, sy, sz, c1, cx, cy, cz);
+    mx = ax * (1.0f - 0.5f) + cx * 0.5f; my = ay * (1.0f - 0.5f) + cy * 0.5f; mz = az * (1.0f - 0.5f) + cz * 0.5f;
+}
+
+__global__ void __launch_bounds__(256) k_cases(const uint4* __restrict__ scene, const float* __restrict__ vox, DevState* st, int level,
+                                               uint8_t* __restrict__ cases, float sx, float sy, float sz, MaskGrid grid, int have_cases) {
     extern __shared__ uint4 smem[];
-    __shared__ McShared mc;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-        mc.packed[i] = c_mc_packed[i]; mc.edgemask[i] = c_mc_edgemask[i]; mc.ntri[i] = c_mc_ntri[i];
-    }
-    const SceneView sc = stage_scene_masked(scene, smem, grid);   // ends with __syncthreads
+    if (have_cases && st->cases_from_refine == 0u) return;   // the last k_refine's lattice signs are the case indices
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
-    const uint32_t ntiles = (n + blockDim.x - 1u) / blockDim.x;   // block-granular tiles (see block_lookback)
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long work = 0;
-    // case indices already written by the last k_refine (from its lattice signs)?  Then the 8 corner evaluations are skipped.
-    const bool reuse_cases = have_cases && st->cases_from_refine == 0u;
+    for (uint32_t v0 = warp_id << 5; v0 < n; v0 += warps_total << 5) {
+        const uint32_t v = v0 + lane;
+        const bool active = v < n;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        if (active) { bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2]; }
+        float cxs[8], cys[8], czs[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) voxel_corner(bx, by, bz, sx, sy, sz, c, cxs[c], cys[c], czs[c]);   // :77-86
+        tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
+        work += (unsigned long long) tile_prims(sc) * 8u * min(32u, n - v0);
+        if (active) {
+            float f[8];
+            eval_scene<8>(sc, cxs, cys, czs, f);
+            uint32_t cube_index = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) cube_index |= (uint32_t) (f[c] <= 0.0f) << c;   // marching_cubes.cu:22
+            cases[v] = (uint8_t) cube_index;
+        }
+    }
+    if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_CLASSIFY], work);
+}
+
+// tri_off[v] = number of triangles of the voxels before v (list order); 4 voxels per thread, block-granular look-back
+__global__ void __launch_bounds__(256) k_tri_offsets(DevState* st, int level, const uint8_t* __restrict__ cases, uint32_t* __restrict__ tri_off,
+                                                     uint32_t epoch, uint64_t* tiles, uint32_t cap_tris) {
+    __shared__ unsigned char s_ntri[256];
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_w[66];
+    __shared__ uint32_t s_w[10];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = c_mc_ntri[i];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = st->level_count[level];
+    const uint32_t per_tile = blockDim.x * 4u;
+    const uint32_t ntiles = (n + per_tile - 1u) / per_tile;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_CLASSIFY], 1u);
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= ntiles) {
-            if (tile == 0 && threadIdx.x == 0) { st->n_tris_raw = 0; st->n_uniq = 0; }
-            if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_CLASSIFY], work);
+            if (tile == 0 && threadIdx.x == 0) st->n_tris_raw = 0;
+            break;
+        }
+        const uint32_t v0 = tile * per_tile + threadIdx.x * 4u;
+        uint32_t c[4] = { 0, 0, 0, 0 };
+        if (v0 + 3u < n) {
+            const uchar4 q = *reinterpret_cast<const uchar4*>(cases + v0);
+            c[0] = s_ntri[q.x]; c[1] = s_ntri[q.y]; c[2] = s_ntri[q.z]; c[3] = s_ntri[q.w];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (v0 + j < n) c[j] = s_ntri[cases[v0 + j]];
+        }
+        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        const uint32_t incl = warp_inclusive_sum(mine, lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t end;
+        const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, end);
+        uint32_t o = base + incl - mine;
+        if (v0 + 3u < n) {
+            *reinterpret_cast<uint4*>(tri_off + v0) = make_uint4(o, o + c[0], o + c[0] + c[1], o + c[0] + c[1] + c[2]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { if (v0 + j < n) tri_off[v0 + j] = o; o += c[j]; }
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            if (end > cap_tris) atomicOr(&st->error_flags, ERR_TRI_CAP);
+            st->n_tris_raw = min(end, cap_tris);
+        }
+    }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
+                                               const uint32_t* __restrict__ tri_off, uint4* table, uint32_t table_mask,
+                                               uint32_t* __restrict__ slot_ref, uint16_t* __restrict__ won, float sx, float sy, float sz) {
+    __shared__ McShared mc;
+    __shared__ uint32_t s_eref[12 * 256];   // [edge][thread]: bank-conflict-free dynamic indexing by edge
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        mc.packed[i] = c_mc_packed[i]; mc.edgemask[i] = c_mc_edgemask[i]; mc.ntri[i] = c_mc_ntri[i];
+    }
+    __syncthreads();
+    if (st->error_flags) return;
+    const uint32_t n = st->level_count[level];
+    bool full = false;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const uint32_t cube_index = cases[v];
+        const uint32_t emask = mc.edgemask[cube_index];
+        uint32_t won_mask = 0;
+        if (emask) {
+            const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
+            // pass 1: start the table lines of all used edges on their way to L2 (the probes below are dependent chains)
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                if (emask & (1u << e)) {
+                    float mx, my, mz;
+                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                    uint32_t kx = __float_as_uint(mx);
+                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
+                    prefetch_l2(table + (hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask));
+                }
+            }
+            // pass 2: find-or-insert; remember the table entry per edge and which ones this voxel created
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                if (emask & (1u << e)) {
+                    float mx, my, mz;
+                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                    uint32_t kx = __float_as_uint(mx);
+                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
+                    bool w;
+                    const uint32_t pos = hash_find_or_insert(table, table_mask, kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
+                    if (pos == 0xFFFFFFFFu) full = true;
+                    if (w) won_mask |= 1u << e;
+                    s_eref[e * 256 + threadIdx.x] = pos;
+                }
+            }
+            const uint32_t ntri = mc.ntri[cube_index];
+            const uint32_t t0 = tri_off[v];
+            const unsigned long long packed = mc.packed[cube_index];
+            for (uint32_t j = 0; j < 3 * ntri; j++) {
+                const uint32_t e = (uint32_t) ((packed >> (4 * j)) & 0xFull);
+                slot_ref[3 * (size_t) t0 + j] = s_eref[e * 256 + threadIdx.x];
+            }
+        }
+        won[v] = (uint16_t) won_mask;
+    }
+    if (full) atomicOr(&st->error_flags, ERR_HASH_FULL);
+}
+
+__global__ void __launch_bounds__(256) k_assign_uids(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
+                                                     const uint32_t* __restrict__ tri_off, const uint16_t* __restrict__ won, uint4* table,
+                                                     const uint32_t* __restrict__ slot_ref, float* __restrict__ ustart, uint32_t cap_uniq,
+                                                     uint32_t epoch, uint64_t* tiles, float sx, float sy, float sz) {
+    __shared__ unsigned long long s_packed[256];
+    __shared__ unsigned char s_ntri[256];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_w[10];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_packed[i] = c_mc_packed[i]; s_ntri[i] = c_mc_ntri[i]; }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = st->level_count[level];
+    const uint32_t ntiles = (n + blockDim.x - 1u) / blockDim.x;
+    const bool bad = st->error_flags != 0u;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_ASSIGN], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles || bad) {
+            if ((tile == 0 || bad) && threadIdx.x == 0) st->n_uniq = 0;
             break;
         }
         const uint32_t v = tile * blockDim.x + threadIdx.x;
-        const bool active = v < n;
-        float bx = 0.f, by = 0.f, bz = 0.f;
-        if (active) { bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2]; }
-        float cxs[8], cys[8], czs[8];
-        uint32_t cube_index = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) voxel_corner(bx, by, bz, sx, sy, sz, c, cxs[c], cys[c], czs[c]);   // :77-86
-        if (reuse_cases) {
-            if (active) cube_index = cases[v];
-        } else {
-            tile_mask_from_box(grid, sc, active, bx, by, bz, bx + sx, by + sy, bz + sz);
-            work += (unsigned long long) tile_prims(sc) * 8u * (uint32_t) __popc(__ballot_sync(0xffffffffu, active));
-            if (active) {
-                float f[8];
-                eval_scene<8>(sc, cxs, cys, czs, f);
-#pragma unroll
-                for (int c = 0; c < 8; c++) cube_index |= (uint32_t) (f[c] <= 0.0f) << c;   // marching_cubes.cu:22
+        const uint32_t wm = v < n ? won[v] : 0u;
+        const uint32_t nwon = __popc(wm);
+        const uint32_t incl = warp_inclusive_sum(nwon, lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t end;
+        const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, end);
+        if (end > cap_uniq) {
+            if (threadIdx.x == 0) atomicOr(&st->error_flags, ERR_UNIQ_CAP);
+        } else if (wm) {
+            const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
+            const uint32_t cube_index = cases[v];
+            const unsigned long long packed = s_packed[cube_index];
+            const uint32_t nslots = 3u * s_ntri[cube_index];
+            const uint32_t t0 = tri_off[v];
+            uint32_t uid = base + incl - nwon;
+            uint32_t m = wm;
+            while (m) {
+                const int e = __ffs((int) m) - 1;
+                m &= m - 1u;
+                float mx, my, mz;
+                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
+                uint32_t j = 0;
+                while (j < nslots && (uint32_t) ((packed >> (4 * j)) & 0xFull) != (uint32_t) e) j++;   // an edge of the case's mask is used by a triangle
+                if (j < nslots) reinterpret_cast<uint32_t*>(table + slot_ref[3 * (size_t) t0 + j])[3] = uid;   // readers come after the kernel boundary
+                uid++;
             }
         }
-        const uint32_t ntri = active ? mc.ntri[cube_index] : 0u;
-        // --- edges: find-or-insert the mid-points; remember the table entry per edge and which ones this lane created
-        const uint32_t emask = active ? mc.edgemask[cube_index] : 0u;
-        uint32_t eref[12];
-        uint32_t won_mask = 0;
-        bool full = false;
-#pragma unroll
-        for (int e = 0; e < 12; e++) {
-            eref[e] = 0xFFFFFFFFu;
-            if (emask & (1u << e)) {
-                // MC_EDGE_TABLE (marching_cubes_constants.cu:3-16)
-                const int c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
-                const int c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
-                // mix(a, b, 0.5f) = a * (1.0f - 0.5f) + b * 0.5f
-                const float mx = cxs[c0] * (1.0f - 0.5f) + cxs[c1] * 0.5f, my = cys[c0] * (1.0f - 0.5f) + cys[c1] * 0.5f,
-                            mz = czs[c0] * (1.0f - 0.5f) + czs[c1] * 0.5f;
-                uint32_t kx = __float_as_uint(mx);
-                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
-                bool won;
-                const uint32_t pos = hash_find_or_insert(table, table_mask, kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &won);
-                if (pos == 0xFFFFFFFFu) full = true;
-                if (won) won_mask |= 1u << e;
-                eref[e] = pos;
-            }
-        }
-        if (__any_sync(0xffffffffu, full) && lane == 0) atomicOr(&st->error_flags, ERR_HASH_FULL);
-        // --- offsets: triangles and new vertex ids, both in list order
-        const uint32_t nwon = __popc(won_mask);
-        const uint32_t tri_incl = warp_inclusive_sum(ntri, lane), uid_incl = warp_inclusive_sum(nwon, lane);
-        const uint32_t tri_total = __shfl_sync(0xffffffffu, tri_incl, 31), uid_total = __shfl_sync(0xffffffffu, uid_incl, 31);
-        uint32_t tri_base, uid_base, tri_end, uid_end;
-        block_lookback2(tiles_tri, tiles_uid, tile, epoch_tri, epoch_uid, tri_total, uid_total, s_w, tri_base, uid_base, tri_end, uid_end);
-        const bool fits = tri_end <= cap_tris && uid_end <= cap_uniq;
-        if (!fits && threadIdx.x == 0) atomicOr(&st->error_flags, tri_end > cap_tris ? ERR_TRI_CAP : ERR_UNIQ_CAP);
-        if (active) {
-            cases[v] = (uint8_t) cube_index;
-            const uint32_t t0 = tri_base + tri_incl - ntri;
-            tri_off[v] = t0;
-            if (fits && !full) {
-                uint32_t uid = uid_base + uid_incl - nwon;
-#pragma unroll
-                for (int e = 0; e < 12; e++) {
-                    if (won_mask & (1u << e)) {
-                        const int c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
-                        const int c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
-                        ustart[3 * (size_t) uid] = cxs[c0] * (1.0f - 0.5f) + cxs[c1] * 0.5f;
-                        ustart[3 * (size_t) uid + 1] = cys[c0] * (1.0f - 0.5f) + cys[c1] * 0.5f;
-                        ustart[3 * (size_t) uid + 2] = czs[c0] * (1.0f - 0.5f) + czs[c1] * 0.5f;
-                        reinterpret_cast<uint32_t*>(table + eref[e])[3] = uid;   // readers come after the kernel boundary
-                        uid++;
-                    }
-                }
-                const unsigned long long packed = mc.packed[cube_index];
-                for (uint32_t j = 0; j < 3 * ntri; j++) {
-                    const int e = (int) ((packed >> (4 * j)) & 0xFull);
-                    uint32_t r = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int q = 0; q < 12; q++) if (q == e) r = eref[q];
-                    slot_ref[3 * (size_t) t0 + j] = r;
-                }
-            }
-        }
-        if (tile == ntiles - 1 && threadIdx.x == 0) {
-            st->n_tris_raw = min(tri_end, cap_tris);
-            st->n_uniq = min(uid_end, cap_uniq);
-        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) st->n_uniq = min(end, cap_uniq);
     }
 }
 
@@ -942,7 +1035,7 @@ __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ s
                 float d = inf, kk = 0.0f;
                 if (active) {
                     const DevPrim c = sc.prims[j];
-                    d = prim_distance(c, cx, cy, cz);
+                    d = prim_distance_cull(c, cx, cy, cz);
                     kk = c.fold == SDM_FOLD_SMOOTH_MIN ? c.k : 0.0f;
                 }
                 const float ub = d + rho;

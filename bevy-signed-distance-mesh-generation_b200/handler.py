@@ -17,6 +17,7 @@ stage in HBM.  There is no CPU fallback: if the library or a CUDA device is miss
 from __future__ import annotations
 
 import ctypes
+import os
 import dataclasses
 import pathlib
 
@@ -85,7 +86,8 @@ ABI_SYMBOLS = [
 
 
 def lib_path() -> pathlib.Path:
-    return _HERE / "libsdfmesh.so"
+    # SDM_LIB: developer override to load another build of the SAME CUDA library (kernel-variant experiments)
+    return pathlib.Path(os.environ["SDM_LIB"]) if os.environ.get("SDM_LIB") else _HERE / "libsdfmesh.so"
 
 
 _lib = None
