@@ -173,6 +173,7 @@ struct SdmHandle {
     uint32_t scene_nprims = 0;          // compiled primitives (skeletons expanded)
     bool mask_capable = false;          // large scene of 1-Lipschitz primitives: per-cell primitive masks are used
     DevBuf<uint32_t> masks_fine, masks_coarse;
+    DevBuf<uint8_t> cell_maybe;         // per fine cell: 0 = provably no zero crossing inside (k_build_masks)
     MaskGrid grid {};                   // grid.enabled == 0 until ensure_masks has built it
     float grid_bb = 0.0f;
     uint32_t grid_init = 0;
@@ -312,8 +313,11 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     // radius = circumsphere of the cell cube (x1.0001) + the empirical_normal stencil reach (2e-3, signed_distance.cu:179)
     //          + slop for the inward-nudged box probes and the domain-face tolerance (2e-3 cell) + 1e-4
     auto rho = [](float cell) { return cell * 0.8660254f * 1.0001f + 0.0021f + 2e-3f * cell + 1e-4f; };
-    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell));
-    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell));
+    CK(h->cell_maybe.reserve((size_t) G * G * G));
+    fine.maybe = nullptr; coarse.maybe = nullptr;
+    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell), nullptr);
+    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell), h->cell_maybe.p);
+    fine.maybe = h->cell_maybe.p;
     mark(h, "k_build_masks_x2");
     h->stats.kernel_launches += 2;
     CK(cudaGetLastError());
@@ -412,7 +416,7 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     if (with_cases) cudaMemsetAsync(&h->state.p->cases_from_refine, 0, 4, h->stream);   // the kernel stores 2 if a lattice is inexact
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
                                                                 next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz, h->grid,
-                                                                with_cases ? h->cases.p : nullptr);
+                                                                with_cases ? h->cases.p : nullptr, h->level == 0 && h->grid.enabled ? 1 : 0);
     h->cases_for_level = with_cases ? h->level + 1 : -1;
     mark(h, "k_refine");
     h->stats.kernel_launches++;
@@ -651,7 +655,7 @@ void sdm_destroy(SdmHandle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int b = 0; b < 2; b++) { if (h->ev_mesh_done[b]) cudaEventDestroy(h->ev_mesh_done[b]); if (h->ev_copy_done[b]) cudaEventDestroy(h->ev_copy_done[b]); }
-    h->masks_fine.release(); h->masks_coarse.release();
+    h->masks_fine.release(); h->masks_coarse.release(); h->cell_maybe.release();
     h->scene.release(); h->vox[0].release(); h->vox[1].release(); h->cases.release(); h->tri_off.release(); h->slot_ref.release();
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();

@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox,
                                                 float* __restrict__ out_vox, DevState* st, int level, uint32_t epoch,
                                                 uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz, MaskGrid grid,
-                                                uint8_t* __restrict__ out_cases) {
+                                                uint8_t* __restrict__ out_cases, int use_cell_flags) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
@@ -140,11 +140,15 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
             by = in_vox[3 * (size_t) (p0 + lane) + 1];
             bz = in_vox[3 * (size_t) (p0 + lane) + 2];
         }
+        // Dense level of a culled scene: a parent inside cells that provably contain no zero crossing has 27 equal signs, so
+        // none of its children survives (is_border, :36-49) - it is not evaluated and does not lengthen the tile's list.
+        const bool eval = active && (!use_cell_flags || box_may_cross(grid, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz));
+        const uint32_t neval = (uint32_t) __popc(__ballot_sync(0xffffffffu, eval));
         // primitives that can matter anywhere inside this tile's parent voxels (edge = 2 * child size)
-        tile_mask_from_box(grid, sc, active, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
-        work += (unsigned long long) tile_prims(sc) * 27u * np;
+        if (neval) tile_mask_from_box(grid, sc, eval, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
+        if (neval) work += (unsigned long long) tile_prims(sc) * 27u * neval;
         uint32_t m27 = 0;
-        if (active) {
+        if (eval) {
 #pragma unroll 1
             for (int a = 0; a < 3; a++) {
                 float px[9], py[9], pz[9], f[9];
@@ -999,7 +1003,8 @@ __global__ void __launch_bounds__(256) k_selftest_math(unsigned long long* __res
 // With parent masks (coarse grid, 4x4x4 fine cells per coarse cell) only primitives of the parent's mask are tested:
 // a primitive outside the parent's mask is already proven droppable on the parent's sphere, which contains the child's.
 __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ scene, uint32_t* __restrict__ out_masks, MaskGrid g,
-                                                     const uint32_t* __restrict__ parent_masks, uint32_t parent_G, float rho) {
+                                                     const uint32_t* __restrict__ parent_masks, uint32_t parent_G, float rho,
+                                                     uint8_t* __restrict__ out_maybe) {
     // the table is read through L1 (each lane reads a different record: from shared memory that would be a 16-way bank
     // conflict, and staging 64 KB per block would cap occupancy)
     const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(scene);
@@ -1055,6 +1060,15 @@ __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ s
                 carry = fminf(carry, total);
             }
             if (wl < g.W) out_masks[(size_t) cell * g.W + wl] = myword;
+        }
+        // Zero-crossing flag.  carry - rho = min_i d_i(c) (a primitive outside the parent's mask is never the nearest one).  For
+        // every p within rho of c:  min_i d_i(p) - kmax <= sd(p) <= min_i d_i(p)  (smooth_min(a,b) <= min(a,b); the fold never
+        // drops more than kmax below the minimum of the distances folded so far, see tile_refine) and |d_i(p) - d_i(c)| <= rho,
+        // so  min_d - rho - kmax > 0  means sd > 0 on the whole cell and  min_d + rho < 0  means sd < 0 on the whole cell.
+        if (out_maybe && lane == 0) {
+            const float min_d = carry - rho;
+            const bool empty = (min_d - rho - hdr.kmax > 1e-4f) || (min_d + rho < -1e-4f);
+            out_maybe[cell] = empty ? 0 : 1;   // NaN: not empty
         }
     }
 }
