@@ -190,6 +190,7 @@ struct SdmHandle {
     // mesh intermediates
     uint32_t cap_tris = 0, cap_uniq = 0, table_entries = 0;
     DevBuf<uint8_t> cases;
+    DevBuf<uint32_t> m27;              // per parent: the 27 lattice signs of the last k_refine
     DevBuf<uint16_t> won;              // per voxel: edges whose vertex-table entry this voxel created
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
     DevBuf<float> ustart, upos, unrm;
@@ -339,6 +340,7 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     for (int i = 0; i < 2; i++) CK(h->vox[i].reserve((size_t) cap_vox * 3));
     CK(h->cases.reserve((size_t) cap_vox + 4));
     CK(h->won.reserve(cap_vox));
+    CK(h->m27.reserve(cap_vox));
     CK(h->tri_off.reserve(cap_vox));
     CK(h->slot_ref.reserve((size_t) h->cap_tris * 3));
     CK(h->tri_uid.reserve((size_t) h->cap_tris * 3));
@@ -414,12 +416,15 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     if (mrc) return mrc;
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
     if (with_cases) cudaMemsetAsync(&h->state.p->cases_from_refine, 0, 4, h->stream);   // the kernel stores 2 if a lattice is inexact
-    k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level,
-                                                                next_epoch(h), h->tiles.p, h->cap_vox, ox, oy, oz, h->grid,
-                                                                with_cases ? h->cases.p : nullptr, h->level == 0 && h->grid.enabled ? 1 : 0);
-    h->cases_for_level = with_cases ? h->level + 1 : -1;
+    k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p,
+                                                                with_cases ? 1 : 0, h->level == 0 && h->grid.enabled ? 1 : 0);
     mark(h, "k_refine");
-    h->stats.kernel_launches++;
+    cudaMemsetAsync(&h->state.p->ticket[TK_REFINE_EMIT], 0, 4, h->stream);
+    k_refine_emit<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cap_vox,
+                                                     ox, oy, oz, h->m27.p, with_cases ? h->cases.p : nullptr);
+    h->cases_for_level = with_cases ? h->level + 1 : -1;
+    mark(h, "k_refine_emit");
+    h->stats.kernel_launches += 2;
     h->cur ^= 1; h->level++;
     h->voxel_size[0] = ox; h->voxel_size[1] = oy; h->voxel_size[2] = oz;
     h->mesh_valid = false;
@@ -660,7 +665,7 @@ void sdm_destroy(SdmHandle* h) {
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
-    h->won.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
+    h->won.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     h->shard_range.release();

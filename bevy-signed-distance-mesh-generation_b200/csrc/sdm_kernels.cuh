@@ -26,7 +26,7 @@ namespace sdm {
 
 namespace cg = cooperative_groups;
 
-enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_COUNT = 24 };
+enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_REFINE_EMIT = 22, TK_COUNT = 24 };
 enum ErrFlag : uint32_t {
     ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u
 };
@@ -104,31 +104,32 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
     return v;
 }
 
-// One warp = one tile of 32 parents, one lane = one parent.  The reference tests the 8 corners of each of the 8 children
-// (<= 64 evaluations, compute_mesh_generation.cu:30-49); the corners are the 27 points of the parent's 3x3x3 lattice
-// (`upper` of child i is `lower` of child i+1: the same float expression base + vec3{i,j,k} * size), so 27 evaluations
-// give the same 64 signs.  They are done as three x-slabs of 9 points held in registers (ILP 9 per lane).
-// Surviving children are appended in the reference's order (n_id = id*8 + i*4 + j*2 + k, :51; Vec::retain is stable,
-// src/cuda/mod.rs:192) at the offset given by a warp scan + decoupled look-back across tiles.
-__global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox,
-                                                float* __restrict__ out_vox, DevState* st, int level, uint32_t epoch,
-                                                uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz, MaskGrid grid,
-                                                uint8_t* __restrict__ out_cases, int use_cell_flags) {
+// Refinement in two kernels.
+// k_refine: one warp = one tile of 32 parents, one lane = one parent.  The reference tests the 8 corners of each of the 8
+// children (<= 64 evaluations, compute_mesh_generation.cu:30-49); the corners are the 27 points of the parent's 3x3x3
+// lattice (`upper` of child i is `lower` of child i+1: the same float expression base + vec3{i,j,k} * size), so 27
+// evaluations give the same 64 signs.  They are done as three x-slabs of 9 points held in registers (ILP 9 per lane).  The
+// kernel only records the 27 signs per parent; tiles need no order, so no warp ever waits for another one (with the ordered
+// append fused in, a third of the kernel's instructions were look-back spins: ncu, profiles/).
+// k_refine_emit: surviving children are appended in the reference's order (n_id = id*8 + i*4 + j*2 + k, :51; Vec::retain
+// is stable, src/cuda/mod.rs:192) at the offset given by a block scan + decoupled look-back across tiles - a streaming pass.
+__global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox, DevState* st, int level,
+                                                float osx, float osy, float osz, MaskGrid grid, uint32_t* __restrict__ out_m27,
+                                                int want_cases, int use_cell_flags) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
-    const uint32_t ntiles = (n + 31u) >> 5;   // warp-granular tiles: the heavy per-tile work hides the look-back walk here
+    const uint32_t ntiles = (n + 31u) >> 5;
     unsigned long long work = 0;
     bool lattice_ok = true;
     while (true) {
         uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&st->ticket[TK_REFINE0 + level], 1u);
+        if (lane == 0) tile = atomicAdd(&st->ticket[TK_REFINE0 + level], 1u);   // dynamic hand-out: tile costs vary with the list lengths
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) {
-            if (tile == 0 && lane == 0) st->level_count[level + 1] = 0;   // empty input: no-op (src/cuda/mod.rs:137)
             if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_REFINE], work);
-            if (out_cases && !__all_sync(0xffffffffu, lattice_ok) && lane == 0) st->cases_from_refine = 2u;
+            if (want_cases && !__all_sync(0xffffffffu, lattice_ok) && lane == 0) st->cases_from_refine = 2u;
             break;
         }
         const uint32_t p0 = tile << 5;
@@ -164,25 +165,9 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
                 for (int q = 0; q < 9; q++) m27 |= (uint32_t) (f[q] <= 0.0f) << (a * 9 + q);   // obj_contains, :8-10
             }
         }
-        uint32_t keep = 0;
         if (active) {
-#pragma unroll
-            for (int ch = 0; ch < 8; ch++) {
-                const uint32_t M = child_mask(ch >> 2, (ch >> 1) & 1, ch & 1);
-                const uint32_t sgn = m27 & M;
-                keep |= (uint32_t) (sgn != 0u && sgn != M) << ch;   // is_border: corners do not all agree (:36-49)
-            }
-        }
-        const uint32_t cnt = __popc(keep);
-        const uint32_t incl = warp_inclusive_sum(cnt, lane);
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
-        const uint32_t block_end = excl_tile + total;
-        uint32_t pos = excl_tile + incl - cnt;
-        if (block_end > cap_vox) {
-            if (lane == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
-        } else {
-            if (out_cases && active) {
+            out_m27[p0 + lane] = m27;   // a skipped parent: 27 equal signs, recorded as "all outside" (no child survives either way)
+            if (want_cases) {
                 // The mesh stage samples child corners at child_base + size (compute_mesh_generation.cu:77-86); the lattice
                 // has base + 2*size where the child is the upper one.  The 27 signs double as the children's corner signs
                 // only if both expressions give the same float on every axis (always true on the dyadic default grid).
@@ -190,6 +175,47 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
                              __float_as_uint((by + osy) + osy) == __float_as_uint(by + 2.0f * osy) &&
                              __float_as_uint((bz + osz) + osz) == __float_as_uint(bz + 2.0f * osz);
             }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
+                                                     uint32_t epoch, uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz,
+                                                     const uint32_t* __restrict__ in_m27, uint8_t* __restrict__ out_cases) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_w[10];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = st->level_count[level];
+    const uint32_t ntiles = (n + blockDim.x - 1u) / blockDim.x;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_REFINE_EMIT], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) {
+            if (tile == 0 && threadIdx.x == 0) st->level_count[level + 1] = 0;   // empty input: no-op (src/cuda/mod.rs:137)
+            break;
+        }
+        const uint32_t p = tile * blockDim.x + threadIdx.x;
+        const bool active = p < n;
+        const uint32_t m27 = active ? in_m27[p] : 0u;
+        uint32_t keep = 0;
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            const uint32_t M = child_mask(ch >> 2, (ch >> 1) & 1, ch & 1);
+            const uint32_t sgn = m27 & M;
+            keep |= (uint32_t) (sgn != 0u && sgn != M) << ch;   // is_border: corners do not all agree (:36-49)
+        }
+        const uint32_t cnt = __popc(keep);
+        const uint32_t incl = warp_inclusive_sum(cnt, lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t block_end;
+        const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, block_end);
+        if (block_end > cap_vox) {
+            if (threadIdx.x == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
+        } else if (keep) {
+            const float bx = in_vox[3 * (size_t) p + 0], by = in_vox[3 * (size_t) p + 1], bz = in_vox[3 * (size_t) p + 2];
+            uint32_t pos = base + incl - cnt;
 #pragma unroll
             for (int ch = 0; ch < 8; ch++) {
                 if (keep & (1u << ch)) {
@@ -211,7 +237,7 @@ __global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene,
                 }
             }
         }
-        if (tile == ntiles - 1 && lane == 0) st->level_count[level + 1] = min(block_end, cap_vox);
+        if (tile == ntiles - 1 && threadIdx.x == 0) st->level_count[level + 1] = min(block_end, cap_vox);
     }
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Developer probe: per-kernel CUDA-event times of one remesh per workload (not the bench)."""
-import sys, time, pathlib
+import sys, time, pathlib, os, ctypes
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import numpy as np
 import bsdmg_b200
@@ -10,6 +10,8 @@ def run(name, scene, bb, init, levels, reps=3):
     h = bsdmg_b200.CudaHandler(0, scene)
     h.set_profiling(True)
     for r in range(reps):
+        if r == reps - 1 and os.environ.get("SDM_PROFILE_LAST"):   # ncu --profile-from-start off: only the last remesh is captured
+            ctypes.CDLL("libcudart.so").cudaProfilerStart()
         t = time.time(); m = h.remesh(bb, init, levels, download=False); wall = time.time() - t
     st = h.stats()
     print(f"== {name}: res {init << levels}^3 voxels {st['level_counts'][:levels+1]} tris {m.triangle_count} verts {m.vertex_count} uniq {st['unique_vertices']} "
