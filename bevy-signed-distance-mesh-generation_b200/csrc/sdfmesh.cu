@@ -191,7 +191,9 @@ struct SdmHandle {
     uint32_t cap_tris = 0, cap_uniq = 0, table_entries = 0;
     DevBuf<uint8_t> cases;
     DevBuf<uint32_t> m27;              // per parent: the 27 lattice signs of the last k_refine
+    DevBuf<uint32_t> uid_base;         // per voxel: id of the first vertex it created
     DevBuf<uint16_t> won;              // per voxel: edges whose vertex-table entry this voxel created
+    DevBuf<uint32_t> vidx;             // per vertex: its index in the welded output
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
     DevBuf<float> ustart, upos, unrm;
     // Mesh outputs are double-buffered: while one mesh is being copied to the host on copy_stream (sdm_mesh_download_async)
@@ -339,7 +341,8 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     h->table_entries = pow2_at_least((uint64_t) h->cap_uniq * 2);
     for (int i = 0; i < 2; i++) CK(h->vox[i].reserve((size_t) cap_vox * 3));
     CK(h->cases.reserve((size_t) cap_vox + 4));
-    CK(h->won.reserve(cap_vox));
+    CK(h->won.reserve((size_t) cap_vox + 4));
+    CK(h->uid_base.reserve((size_t) cap_vox + 4));
     CK(h->m27.reserve(cap_vox));
     CK(h->tri_off.reserve(cap_vox));
     CK(h->slot_ref.reserve((size_t) h->cap_tris * 3));
@@ -351,6 +354,7 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     CK(h->tri_prefix.reserve(((size_t) h->cap_tris + 31) / 32 + 32));
     CK(h->first_slot.reserve(h->cap_uniq));
     CK(h->wref.reserve(h->cap_uniq));
+    CK(h->vidx.reserve(h->cap_uniq));
     CK(h->ustart.reserve((size_t) h->cap_uniq * 3));
     CK(h->upos.reserve((size_t) h->cap_uniq * 3));
     CK(h->unrm.reserve((size_t) h->cap_uniq * 3));
@@ -440,7 +444,7 @@ int enqueue_weld_clears(SdmHandle* h, bool clear_first_slot) {
 }
 
 // classify+edges -> project (+tail) -> normals -> orient: everything that needs only this handle's voxels
-int enqueue_mesh_local(SdmHandle* h) {
+int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     int mrc = ensure_masks_any(h);
     if (mrc) return mrc;
     const float sx = h->voxel_size[0], sy = h->voxel_size[1], sz = h->voxel_size[2];
@@ -462,10 +466,11 @@ int enqueue_mesh_local(SdmHandle* h) {
     mark(h, "k_cases+k_tri_offsets");
     k_edges<<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->won.p, sx, sy, sz);
     mark(h, "k_edges");
-    k_assign_uids<<<h->g_light, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->won.p, h->table1.p, h->slot_ref.p, h->ustart.p, h->cap_uniq,
-                                            next_epoch(h), h->tiles2.p, sx, sy, sz);
+    k_uid_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->won.p, h->uid_base.p, next_epoch(h), h->tiles2.p, h->cap_uniq);
+    k_assign_uids<<<h->g_light * 2, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->won.p, h->uid_base.p, h->table1.p, h->slot_ref.p,
+                                                h->ustart.p, sx, sy, sz);
     mark(h, "k_assign_uids");
-    h->stats.kernel_launches += 3;
+    h->stats.kernel_launches += 4;
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
@@ -474,7 +479,8 @@ int enqueue_mesh_local(SdmHandle* h) {
     mark(h, "k_project");
     k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid);
     mark(h, "k_project_tail");
-    k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid);
+    k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid,
+                                                        fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p);
     mark(h, "k_vertex_normals");
     k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
                                                 h->tri_valid_bits.p, h->grid);
@@ -485,22 +491,24 @@ int enqueue_mesh_local(SdmHandle* h) {
 }
 
 // the reference-order weld over (upos, unrm, tri_uid, first_slot, tri_valid_bits) and the counters in DevState
-int enqueue_weld(SdmHandle* h) {
+int enqueue_weld(SdmHandle* h, bool keys_inserted) {
     cudaStream_t s = h->stream;
     const int b = h->out_sel;
     CK(cudaStreamWaitEvent(s, h->ev_copy_done[b], 0));   // the download of the mesh that used this set two remeshes ago
-    k_weld_insert<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->first_slot.p, h->table2.p, h->table_entries, h->wref.p, h->cap_uniq);
-    mark(h, "k_weld_insert");
+    if (!keys_inserted) {
+        k_weld_keys<<<h->g_light, 256, 0, s>>>(h->state.p, h->upos.p, h->table2.p, h->table_entries, h->wref.p, h->cap_uniq);
+        h->stats.kernel_launches++;
+    }
+    k_weld_min<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->cap_uniq);
     k_weld_mark<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->cap_uniq);
-    mark(h, "k_weld_mark");
+    mark(h, "k_weld_min+mark");
     k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_bits.p, h->first_prefix.p, 0, next_epoch(h), h->tiles.p);
     k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_valid_bits.p, h->tri_prefix.p, 1, next_epoch(h), h->tiles.p);
     mark(h, "k_bitscan_x2");
     k_emit_vertices<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_slot.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
-                                                h->upos.p, h->unrm.p, h->out_pos[b].p, h->out_nrm[b].p, h->cap_uniq);
+                                                h->upos.p, h->unrm.p, h->out_pos[b].p, h->out_nrm[b].p, h->vidx.p, h->cap_uniq);
     mark(h, "k_emit_vertices");
-    k_emit_indices<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p,
-                                               h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx[b].p);
+    k_emit_indices<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->vidx.p, h->tri_valid_bits.p, h->tri_prefix.p, h->out_idx[b].p);
     mark(h, "k_emit_indices");
     CK(cudaEventRecord(h->ev_mesh_done[b], s));
     h->stats.kernel_launches += 6;
@@ -509,9 +517,9 @@ int enqueue_weld(SdmHandle* h) {
 }
 
 int enqueue_mesh(SdmHandle* h) {
-    int rc = enqueue_mesh_local(h);
+    int rc = enqueue_mesh_local(h, true);
     if (rc) return rc;
-    return enqueue_weld(h);
+    return enqueue_weld(h, true);
 }
 
 // Copies DevState to the pinned host mirror and waits.  Returns the device-side error flags through *flags.
@@ -665,7 +673,7 @@ void sdm_destroy(SdmHandle* h) {
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
-    h->won.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
+    h->won.release(); h->vidx.release(); h->uid_base.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     h->shard_range.release();
@@ -1059,7 +1067,7 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
             rc = enqueue_refine(h, l + 1 == p.levels);
             if (rc) return rc;
         }
-        rc = enqueue_mesh_local(h);
+        rc = enqueue_mesh_local(h, false);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaMemcpyAsync(h->host_range, h->shard_range.p, 12, cudaMemcpyDeviceToHost, h->stream));
@@ -1147,7 +1155,7 @@ int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangl
     if (rc) return rc;
     k_first_slot_merged<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_uid.p, h->first_slot.p, h->tri_valid_bits.p, h->own_tris);
     h->stats.kernel_launches++;
-    rc = enqueue_weld(h);
+    rc = enqueue_weld(h, false);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, s));
     uint32_t flags = 0;

@@ -41,7 +41,7 @@ struct DevState {
     uint32_t ticket[TK_COUNT];
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
     uint32_t cases_from_refine; // 0: the case indices written by the last k_refine are valid; 2: a parent's lattice was inexact
-    uint32_t pad1;
+    uint32_t weld_dups;         // vertices whose quantised weld key was already in the table (0: the weld merges nothing)
     unsigned long long cull_tiles, cull_prims, cull_cands, cull_fallbacks;   // k_orient's tile culling statistics
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
@@ -409,18 +409,15 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
     if (full) atomicOr(&st->error_flags, ERR_HASH_FULL);
 }
 
-__global__ void __launch_bounds__(256) k_assign_uids(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
-                                                     const uint32_t* __restrict__ tri_off, const uint16_t* __restrict__ won, uint4* table,
-                                                     const uint32_t* __restrict__ slot_ref, float* __restrict__ ustart, uint32_t cap_uniq,
-                                                     uint32_t epoch, uint64_t* tiles, float sx, float sy, float sz) {
-    __shared__ unsigned long long s_packed[256];
-    __shared__ unsigned char s_ntri[256];
+// uid_base[v] = number of vertices created by the voxels before v (list order); same streaming scan as k_tri_offsets
+__global__ void __launch_bounds__(256) k_uid_offsets(DevState* st, int level, const uint16_t* __restrict__ won, uint32_t* __restrict__ uid_base,
+                                                     uint32_t epoch, uint64_t* tiles, uint32_t cap_uniq) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_w[10];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_packed[i] = c_mc_packed[i]; s_ntri[i] = c_mc_ntri[i]; }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
-    const uint32_t ntiles = (n + blockDim.x - 1u) / blockDim.x;
+    const uint32_t per_tile = blockDim.x * 4u;
+    const uint32_t ntiles = (n + per_tile - 1u) / per_tile;
     const bool bad = st->error_flags != 0u;
     while (true) {
         __syncthreads();
@@ -431,36 +428,65 @@ __global__ void __launch_bounds__(256) k_assign_uids(const float* __restrict__ v
             if ((tile == 0 || bad) && threadIdx.x == 0) st->n_uniq = 0;
             break;
         }
-        const uint32_t v = tile * blockDim.x + threadIdx.x;
-        const uint32_t wm = v < n ? won[v] : 0u;
-        const uint32_t nwon = __popc(wm);
-        const uint32_t incl = warp_inclusive_sum(nwon, lane);
+        const uint32_t v0 = tile * per_tile + threadIdx.x * 4u;
+        uint32_t c[4] = { 0, 0, 0, 0 };
+        if (v0 + 3u < n) {
+            const ushort4 q = *reinterpret_cast<const ushort4*>(won + v0);
+            c[0] = __popc(q.x); c[1] = __popc(q.y); c[2] = __popc(q.z); c[3] = __popc(q.w);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (v0 + j < n) c[j] = __popc(won[v0 + j]);
+        }
+        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        const uint32_t incl = warp_inclusive_sum(mine, lane);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t end;
         const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, end);
-        if (end > cap_uniq) {
-            if (threadIdx.x == 0) atomicOr(&st->error_flags, ERR_UNIQ_CAP);
-        } else if (wm) {
-            const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
-            const uint32_t cube_index = cases[v];
-            const unsigned long long packed = s_packed[cube_index];
-            const uint32_t nslots = 3u * s_ntri[cube_index];
-            const uint32_t t0 = tri_off[v];
-            uint32_t uid = base + incl - nwon;
-            uint32_t m = wm;
-            while (m) {
-                const int e = __ffs((int) m) - 1;
-                m &= m - 1u;
-                float mx, my, mz;
-                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
-                uint32_t j = 0;
-                while (j < nslots && (uint32_t) ((packed >> (4 * j)) & 0xFull) != (uint32_t) e) j++;   // an edge of the case's mask is used by a triangle
-                if (j < nslots) reinterpret_cast<uint32_t*>(table + slot_ref[3 * (size_t) t0 + j])[3] = uid;   // readers come after the kernel boundary
-                uid++;
-            }
+        uint32_t o = base + incl - mine;
+        if (v0 + 3u < n) {
+            *reinterpret_cast<uint4*>(uid_base + v0) = make_uint4(o, o + c[0], o + c[0] + c[1], o + c[0] + c[1] + c[2]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { if (v0 + j < n) uid_base[v0 + j] = o; o += c[j]; }
         }
-        if (tile == ntiles - 1 && threadIdx.x == 0) st->n_uniq = min(end, cap_uniq);
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            if (end > cap_uniq) atomicOr(&st->error_flags, ERR_UNIQ_CAP);
+            st->n_uniq = min(end, cap_uniq);
+        }
+    }
+}
+
+// start points and ids of the vertices each voxel created (no ordering between voxels any more: plain grid-stride loop)
+__global__ void __launch_bounds__(256) k_assign_uids(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
+                                                     const uint32_t* __restrict__ tri_off, const uint16_t* __restrict__ won,
+                                                     const uint32_t* __restrict__ uid_base, uint4* table, const uint32_t* __restrict__ slot_ref,
+                                                     float* __restrict__ ustart, float sx, float sy, float sz) {
+    __shared__ unsigned long long s_packed[256];
+    __shared__ unsigned char s_ntri[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_packed[i] = c_mc_packed[i]; s_ntri[i] = c_mc_ntri[i]; }
+    __syncthreads();
+    if (st->error_flags) return;
+    const uint32_t n = st->level_count[level];
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        uint32_t m = won[v];
+        if (!m) continue;
+        const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
+        const uint32_t cube_index = cases[v];
+        const unsigned long long packed = s_packed[cube_index];
+        const uint32_t nslots = 3u * s_ntri[cube_index];
+        const uint32_t t0 = tri_off[v];
+        uint32_t uid = uid_base[v];
+        while (m) {
+            const int e = __ffs((int) m) - 1;
+            m &= m - 1u;
+            float mx, my, mz;
+            edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+            ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
+            uint32_t j = 0;
+            while (j < nslots && (uint32_t) ((packed >> (4 * j)) & 0xFull) != (uint32_t) e) j++;   // an edge of the case's mask is used by a triangle
+            if (j < nslots) reinterpret_cast<uint32_t*>(table + slot_ref[3 * (size_t) t0 + j])[3] = uid;   // readers come after the kernel boundary
+            uid++;
+        }
     }
 }
 
@@ -482,7 +508,7 @@ __global__ void __launch_bounds__(256) k_clear_weld_state(DevState* st, uint32_t
     const uint32_t ts = weld_table_size(nu, max_entries);
     const uint4 empty = make_uint4(SDM_HASH_EMPTY, SDM_HASH_EMPTY, SDM_HASH_EMPTY, SDM_HASH_EMPTY);
     for (uint32_t i = tid; i < ts; i += stride) table2[i] = empty;
-    if (tid == 0) { st->n_tris_out = 0; st->n_verts_out = 0; st->ticket[TK_SCAN_FIRST] = 0; st->ticket[TK_SCAN_TRI] = 0; st->ticket[TK_PROJECT] = 0; st->n_stragglers = 0; st->ticket[TK_TAIL] = 0; }
+    if (tid == 0) { st->n_tris_out = 0; st->n_verts_out = 0; st->ticket[TK_SCAN_FIRST] = 0; st->ticket[TK_SCAN_TRI] = 0; st->ticket[TK_PROJECT] = 0; st->n_stragglers = 0; st->ticket[TK_TAIL] = 0; st->weld_dups = 0; }
 }
 
 // closest_surface_point per distinct mid-point (signed_distance.cu:227-240), bulk phase: one lane per vertex; lanes that
@@ -648,20 +674,40 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_TAIL], work);
 }
 
+// Inserts vertex u's quantised weld key (src/cuda/mod.rs:270) into the key table with value 0xFFFFFFFF ("no slot yet");
+// returns the entry, counts vertices that met an existing key.
+__device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* __restrict__ upos, uint32_t u, uint4* table, uint32_t table_mask) {
+    const uint32_t kx = weld_key_component(upos[3 * (size_t) u]);
+    const uint32_t ky = weld_key_component(upos[3 * (size_t) u + 1]);
+    const uint32_t kz = weld_key_component(upos[3 * (size_t) u + 2]);
+    bool won;
+    const uint32_t pos = hash_find_or_insert(table, table_mask, kx, ky, kz, 0xFFFFFFFFu, &won);
+    if (pos == 0xFFFFFFFFu) atomicOr(&st->error_flags, ERR_HASH_FULL);
+    else if (!won) atomicAdd(&st->weld_dups, 1u);
+    return pos;
+}
+
+// empirical_normal per projected vertex.  weld_table != nullptr: the vertex's weld key is inserted here as well - a random
+// DRAM access per vertex that is free while the SM is busy with the twelve evaluations (as a kernel of its own it took a
+// third of this kernel's time doing nothing but waiting for memory).
 __global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
-                                                        float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid) {
+                                                        float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
+                                                        uint32_t weld_max_entries, uint32_t* __restrict__ wref) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags) return;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t table_mask = weld_table_size(n, weld_max_entries) - 1u;   // same size k_clear_weld_state cleared
     unsigned long long work = 0;
     for (uint32_t u0 = warp_id << 5; u0 < n; u0 += warps_total << 5) {   // warp-uniform trip count (tile masks are warp collectives)
         const uint32_t u = u0 + lane;
         const bool active = u < n;
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
+        if (weld_table && active) wref[u] = weld_insert_key(st, upos, u, weld_table, table_mask);
         tile_mask_from_point(grid, sc, active, x, y, z);
         work += (unsigned long long) tile_prims(sc) * 12u * min(32u, n - u0);
         if (active) {
@@ -731,37 +777,39 @@ __global__ void __launch_bounds__(128) k_orient(const uint4* __restrict__ scene,
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_ORIENT], work);
 }
 
-// Weld, step 1: every vertex that is referenced by a kept triangle enters the key table with the smallest slot
-// id (3*triangle + corner, post-flip order) at which it occurs; the table keeps the minimum per key.
-__global__ void __launch_bounds__(256) k_weld_insert(DevState* st, const float* __restrict__ upos, const uint32_t* __restrict__ first_slot,
-                                                     uint4* table, uint32_t max_entries, uint32_t* __restrict__ wref, uint32_t cap_uniq) {
+// The reference-order weld (src/cuda/mod.rs:263-296).  A vertex's key entry is created by weld_insert_key (fused into
+// k_vertex_normals, or k_weld_keys for a merged multi-shard list); first_slot[u] = smallest slot id (3*triangle + corner,
+// post-flip order) at which vertex u occurs in a kept triangle (k_orient).
+//   * weld_dups == 0 (the usual case): all keys are distinct, every referenced vertex is its key's first occurrence, and no
+//     kernel below touches the key table again;
+//   * otherwise k_weld_min leaves each key's smallest slot in its entry, and the vertex whose first slot equals that
+//     minimum is the key's first occurrence in the reference's scan order.
+__global__ void __launch_bounds__(256) k_weld_keys(DevState* st, const float* __restrict__ upos, uint4* table, uint32_t max_entries,
+                                                   uint32_t* __restrict__ wref, uint32_t cap_uniq) {
     const uint32_t n = min(st->n_uniq, cap_uniq);
     if (st->error_flags) return;
     const uint32_t table_mask = weld_table_size(n, max_entries) - 1u;   // same size k_clear_weld_state cleared
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) wref[u] = weld_insert_key(st, upos, u, table, table_mask);
+}
+__global__ void __launch_bounds__(256) k_weld_min(DevState* st, const uint32_t* __restrict__ first_slot, uint4* table,
+                                                  const uint32_t* __restrict__ wref, uint32_t cap_uniq) {
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags || st->weld_dups == 0u) return;
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
         const uint32_t fs = first_slot[u];
-        if (fs == 0xFFFFFFFFu) { wref[u] = 0xFFFFFFFFu; continue; }
-        const uint32_t kx = weld_key_component(upos[3 * (size_t) u]);
-        const uint32_t ky = weld_key_component(upos[3 * (size_t) u + 1]);
-        const uint32_t kz = weld_key_component(upos[3 * (size_t) u + 2]);
-        bool won;
-        const uint32_t pos = hash_find_or_insert(table, table_mask, kx, ky, kz, fs, &won);
-        if (pos == 0xFFFFFFFFu) { atomicOr(&st->error_flags, ERR_HASH_FULL); wref[u] = 0xFFFFFFFFu; continue; }
-        if (!won) atomicMin(reinterpret_cast<uint32_t*>(table + pos) + 3, fs);
-        wref[u] = pos;
+        if (fs != 0xFFFFFFFFu) atomicMin(reinterpret_cast<uint32_t*>(table + wref[u]) + 3, fs);
     }
 }
-// Weld, step 2: the vertex whose first slot equals its key's minimum is the key's first occurrence in the
-// reference's scan order; mark that slot.
+// marks the slot of every key's first occurrence
 __global__ void __launch_bounds__(256) k_weld_mark(DevState* st, const uint32_t* __restrict__ first_slot, const uint4* __restrict__ table,
                                                    const uint32_t* __restrict__ wref, uint32_t* first_bits, uint32_t cap_uniq) {
     const uint32_t n = min(st->n_uniq, cap_uniq);
     if (st->error_flags) return;
+    const bool dups = st->weld_dups != 0u;
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
-        const uint32_t r = wref[u];
-        if (r == 0xFFFFFFFFu) continue;
         const uint32_t fs = first_slot[u];
-        if (reinterpret_cast<const uint32_t*>(table + r)[3] == fs) atomicOr(first_bits + (fs >> 5), 1u << (fs & 31u));
+        if (fs == 0xFFFFFFFFu) continue;
+        if (!dups || reinterpret_cast<const uint32_t*>(table + wref[u])[3] == fs) atomicOr(first_bits + (fs >> 5), 1u << (fs & 31u));
     }
 }
 
@@ -803,41 +851,40 @@ __device__ __forceinline__ uint32_t bit_rank(const uint32_t* __restrict__ bits, 
     return word_prefix[i >> 5] + (uint32_t) __popc(bits[i >> 5] & ((1u << (i & 31u)) - 1u));
 }
 
+// vidx[u] = output index of vertex u (rank of its key's first slot); the first occurrence also writes position AND normal
+// (src/cuda/mod.rs:279-284)
 __global__ void __launch_bounds__(256) k_emit_vertices(DevState* st, const uint32_t* __restrict__ first_slot, const uint4* __restrict__ table,
                                                        const uint32_t* __restrict__ wref, const uint32_t* __restrict__ first_bits,
                                                        const uint32_t* __restrict__ first_prefix, const float* __restrict__ upos,
                                                        const float* __restrict__ unrm, float* __restrict__ out_pos, float* __restrict__ out_nrm,
-                                                       uint32_t cap_uniq) {
+                                                       uint32_t* __restrict__ vidx, uint32_t cap_uniq) {
     const uint32_t n = min(st->n_uniq, cap_uniq);
     if (st->error_flags) return;
+    const bool dups = st->weld_dups != 0u;
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
-        const uint32_t r = wref[u];
-        if (r == 0xFFFFFFFFu) continue;
         const uint32_t fs = first_slot[u];
-        if (reinterpret_cast<const uint32_t*>(table + r)[3] != fs) continue;
-        const uint32_t rank = bit_rank(first_bits, first_prefix, fs);
+        if (fs == 0xFFFFFFFFu) continue;   // not referenced by a kept triangle: never read through vidx either
+        const uint32_t kfs = dups ? reinterpret_cast<const uint32_t*>(table + wref[u])[3] : fs;
+        const uint32_t rank = bit_rank(first_bits, first_prefix, kfs);
+        vidx[u] = rank;
+        if (kfs != fs) continue;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            out_pos[3 * (size_t) rank + c] = upos[3 * (size_t) u + c];   // first occurrence decides position AND normal
-            out_nrm[3 * (size_t) rank + c] = unrm[3 * (size_t) u + c];   // (src/cuda/mod.rs:279-284)
+            out_pos[3 * (size_t) rank + c] = upos[3 * (size_t) u + c];
+            out_nrm[3 * (size_t) rank + c] = unrm[3 * (size_t) u + c];
         }
     }
 }
-__global__ void __launch_bounds__(256) k_emit_indices(DevState* st, const uint32_t* __restrict__ tri_uid, const uint4* __restrict__ table,
-                                                      const uint32_t* __restrict__ wref, const uint32_t* __restrict__ first_bits,
-                                                      const uint32_t* __restrict__ first_prefix, const uint32_t* __restrict__ tri_valid_bits,
-                                                      const uint32_t* __restrict__ tri_prefix, uint32_t* __restrict__ out_idx) {
+__global__ void __launch_bounds__(256) k_emit_indices(DevState* st, const uint32_t* __restrict__ tri_uid, const uint32_t* __restrict__ vidx,
+                                                      const uint32_t* __restrict__ tri_valid_bits, const uint32_t* __restrict__ tri_prefix,
+                                                      uint32_t* __restrict__ out_idx) {
     const uint32_t T = st->n_tris_raw;
     if (st->error_flags) return;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
         if (!((tri_valid_bits[t >> 5] >> (t & 31u)) & 1u)) continue;
         const uint32_t ot = bit_rank(tri_valid_bits, tri_prefix, t);
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const uint32_t u = tri_uid[3 * (size_t) t + j];
-            const uint32_t fs = reinterpret_cast<const uint32_t*>(table + wref[u])[3];
-            out_idx[3 * (size_t) ot + j] = bit_rank(first_bits, first_prefix, fs);
-        }
+        for (int j = 0; j < 3; j++) out_idx[3 * (size_t) ot + j] = vidx[tri_uid[3 * (size_t) t + j]];
     }
 }
 
