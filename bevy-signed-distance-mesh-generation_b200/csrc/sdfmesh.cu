@@ -193,6 +193,7 @@ struct SdmHandle {
     DevBuf<uint32_t> m27;              // per parent: the 27 lattice signs of the last k_refine
     DevBuf<uint32_t> uid_base;         // per voxel: id of the first vertex it created
     DevBuf<uint16_t> won;              // per voxel: edges whose vertex-table entry this voxel created
+    DevBuf<uint32_t> entry_uid;        // per vertex-table entry: the id of its vertex
     DevBuf<uint32_t> vidx;             // per vertex: its index in the welded output
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
     DevBuf<float> ustart, upos, unrm;
@@ -360,6 +361,7 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     CK(h->unrm.reserve((size_t) h->cap_uniq * 3));
     for (int b = 0; b < 2; b++) { CK(h->out_pos[b].reserve((size_t) h->cap_uniq * 3)); CK(h->out_nrm[b].reserve((size_t) h->cap_uniq * 3)); }
     CK(h->table1.reserve(h->table_entries));
+    CK(h->entry_uid.reserve(h->table_entries));
     CK(h->table2.reserve(h->table_entries));
     const size_t max_tiles = std::max<size_t>(((size_t) h->cap_tris * 3 / 32 + 31) / 32, (size_t) cap_vox / 32) + 64;
     const size_t old_tiles = h->tiles.n;
@@ -467,7 +469,7 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     k_edges<<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->won.p, sx, sy, sz);
     mark(h, "k_edges");
     k_uid_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->won.p, h->uid_base.p, next_epoch(h), h->tiles2.p, h->cap_uniq);
-    k_assign_uids<<<h->g_light * 2, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->won.p, h->uid_base.p, h->table1.p, h->slot_ref.p,
+    k_assign_uids<<<h->g_light * 2, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->won.p, h->uid_base.p, h->entry_uid.p, h->slot_ref.p,
                                                 h->ustart.p, sx, sy, sz);
     mark(h, "k_assign_uids");
     h->stats.kernel_launches += 4;
@@ -482,7 +484,7 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid,
                                                         fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p);
     mark(h, "k_vertex_normals");
-    k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->table1.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
+    k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
                                                 h->tri_valid_bits.p, h->grid);
     mark(h, "k_orient");
     h->stats.kernel_launches += 5;
@@ -673,7 +675,7 @@ void sdm_destroy(SdmHandle* h) {
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
-    h->won.release(); h->vidx.release(); h->uid_base.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
+    h->won.release(); h->entry_uid.release(); h->vidx.release(); h->uid_base.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     h->shard_range.release();
