@@ -113,7 +113,10 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 // append fused in, a third of the kernel's instructions were look-back spins: ncu, profiles/).
 // k_refine_emit: surviving children are appended in the reference's order (n_id = id*8 + i*4 + j*2 + k, :51; Vec::retain
 // is stable, src/cuda/mod.rs:192) at the offset given by a block scan + decoupled look-back across tiles - a streaming pass.
-__global__ void __launch_bounds__(256) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox, DevState* st, int level,
+#ifndef SDM_REFINE_MINB
+#define SDM_REFINE_MINB 3
+#endif
+__global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox, DevState* st, int level,
                                                 float osx, float osy, float osz, MaskGrid grid, uint32_t* __restrict__ out_m27,
                                                 int want_cases, int use_cell_flags) {
     extern __shared__ uint4 smem[];
@@ -696,7 +699,10 @@ __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* _
 // empirical_normal per projected vertex.  weld_table != nullptr: the vertex's weld key is inserted here as well - a random
 // DRAM access per vertex that is free while the SM is busy with the twelve evaluations (as a kernel of its own it took a
 // third of this kernel's time doing nothing but waiting for memory).
-__global__ void __launch_bounds__(128) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
+#ifndef SDM_NRM_MINB
+#define SDM_NRM_MINB 6
+#endif
+__global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
                                                         float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
                                                         uint32_t weld_max_entries, uint32_t* __restrict__ wref) {
     extern __shared__ uint4 smem[];
