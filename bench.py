@@ -303,7 +303,9 @@ def main():
                     "peak_source": f"148 SM x 128 FP32 lanes x {sm_max_mhz:.0f} MHz, one op per lane-cycle (no FMA: -fmad=false is part of the parity contract)",
                     "algorithmic_ops_per_prim_point": ops_pp, "prim_point_evals_per_launch": work, "avg_launch_ms": kavg[top],
                     "share_of_step": kavg[top] / step_sum}
-        emit_bytes = vert_count * (24 + 24 + 4 + 4 + 16) + tri_count * (12 + 12 + 3 * 24)
+        # k_emit_vertices: per vertex first_slot 4 + two bit-rank words 8 + position/normal in 24 and out 24 + output index 4;
+        # k_emit_indices: per triangle three vertex ids 12 + three output-index gathers 12 + three indices out 12
+        emit_bytes = vert_count * (4 + 8 + 24 + 24 + 4) + tri_count * (12 + 12 + 12)
         if "k_emit_vertices" in kavg and "k_emit_indices" in kavg:
             t_emit = (kavg["k_emit_vertices"] + kavg["k_emit_indices"]) * 1e-3
             roofline_hbm = {"kernel": "k_emit_vertices+k_emit_indices", "bound": "hbm", "achieved": emit_bytes / t_emit / 1e9, "peak": hbm_peak,

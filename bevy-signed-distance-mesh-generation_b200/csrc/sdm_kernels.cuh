@@ -182,6 +182,17 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
     }
 }
 
+__device__ __forceinline__ uint32_t refine_keep_mask(uint32_t m27) {
+    uint32_t keep = 0;
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) {
+        const uint32_t M = child_mask(ch >> 2, (ch >> 1) & 1, ch & 1);
+        const uint32_t sgn = m27 & M;
+        keep |= (uint32_t) (sgn != 0u && sgn != M) << ch;   // is_border: corners do not all agree (:36-49)
+    }
+    return keep;
+}
+// one parent per thread: a warp's children land in one contiguous run (4 parents per thread made the stores strided: slower)
 __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
                                                      uint32_t epoch, uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz,
                                                      const uint32_t* __restrict__ in_m27, uint8_t* __restrict__ out_cases) {
@@ -373,31 +384,31 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
         uint32_t won_mask = 0;
         if (emask) {
             const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
+            // Both passes walk the set bits of the case's edge mask (4 edges on average; unrolled over all 12, the warp ran
+            // every edge's code because some lane always uses it).
             // pass 1: start the table lines of all used edges on their way to L2 (the probes below are dependent chains)
-#pragma unroll
-            for (int e = 0; e < 12; e++) {
-                if (emask & (1u << e)) {
-                    float mx, my, mz;
-                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                    uint32_t kx = __float_as_uint(mx);
-                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
-                    prefetch_l2(table + (hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask));
-                }
+            for (uint32_t m = emask; m; m &= m - 1u) {
+                const int e = __ffs((int) m) - 1;
+                float mx, my, mz;
+                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                uint32_t kx = __float_as_uint(mx);
+                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
+                const uint32_t pos0 = hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask;
+                prefetch_l2(table + pos0);
+                s_eref[e * 256 + threadIdx.x] = pos0;
             }
-            // pass 2: find-or-insert; remember the table entry per edge and which ones this voxel created
-#pragma unroll
-            for (int e = 0; e < 12; e++) {
-                if (emask & (1u << e)) {
-                    float mx, my, mz;
-                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                    uint32_t kx = __float_as_uint(mx);
-                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
-                    bool w;
-                    const uint32_t pos = hash_find_or_insert(table, table_mask, kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
-                    if (pos == 0xFFFFFFFFu) full = true;
-                    if (w) won_mask |= 1u << e;
-                    s_eref[e * 256 + threadIdx.x] = pos;
-                }
+            // pass 2: find-or-insert from the stored start position; remember the entry per edge and which ones this voxel created
+            for (uint32_t m = emask; m; m &= m - 1u) {
+                const int e = __ffs((int) m) - 1;
+                float mx, my, mz;
+                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                uint32_t kx = __float_as_uint(mx);
+                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
+                bool w;
+                const uint32_t pos = hash_probe_from(table, table_mask, s_eref[e * 256 + threadIdx.x], kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
+                if (pos == 0xFFFFFFFFu) full = true;
+                if (w) won_mask |= 1u << e;
+                s_eref[e * 256 + threadIdx.x] = pos;
             }
             const uint32_t ntri = mc.ntri[cube_index];
             const uint32_t t0 = tri_off[v];
@@ -829,33 +840,47 @@ __global__ void __launch_bounds__(256) k_weld_mark(DevState* st, const uint32_t*
 // which: 0 -> bits cover 3*n_tris_raw slots, total to n_verts_out; 1 -> bits cover n_tris_raw, total to n_tris_out.
 __global__ void __launch_bounds__(256) k_bitscan(DevState* st, const uint32_t* __restrict__ bits, uint32_t* __restrict__ word_prefix,
                                                  int which, uint32_t epoch, uint64_t* tiles) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_w[10];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t nbits = which == 0 ? 3u * st->n_tris_raw : st->n_tris_raw;
     const uint32_t nwords = (nbits + 31u) >> 5;
-    const uint32_t ntiles = (nwords + 31u) >> 5;
+    const uint32_t per_tile = blockDim.x * 4u;   // 4 consecutive words per thread
+    const uint32_t ntiles = (nwords + per_tile - 1u) / per_tile;
     uint32_t* total_out = which == 0 ? &st->n_verts_out : &st->n_tris_out;
     const int tk = which == 0 ? TK_SCAN_FIRST : TK_SCAN_TRI;
     const bool bad = st->error_flags != 0;
     while (true) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&st->ticket[tk], 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[tk], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
         if (tile >= ntiles || bad) {
-            if ((tile == 0 || bad) && lane == 0) *total_out = 0;
+            if ((tile == 0 || bad) && threadIdx.x == 0) *total_out = 0;
             break;
         }
-        const uint32_t w = (tile << 5) + lane;
-        const uint32_t cnt = w < nwords ? (uint32_t) __popc(bits[w]) : 0u;
-        uint32_t incl = cnt;
+        const uint32_t w0 = tile * per_tile + threadIdx.x * 4u;
+        uint32_t c[4] = { 0, 0, 0, 0 };
+        if (w0 + 3u < nwords) {   // (the bit arrays are padded by 32 words, but stay within the words that were cleared)
+            const uint4 q = *reinterpret_cast<const uint4*>(bits + w0);
+            c[0] = __popc(q.x); c[1] = __popc(q.y); c[2] = __popc(q.z); c[3] = __popc(q.w);
+        } else {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t) o) incl += v;
+            for (int j = 0; j < 4; j++) if (w0 + j < nwords) c[j] = __popc(bits[w0 + j]);
         }
+        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        const uint32_t incl = warp_inclusive_sum(mine, lane);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t excl_tile = warp_lookback(tiles, tile, epoch, total);
-        if (w < nwords) word_prefix[w] = excl_tile + incl - cnt;
-        if (tile == ntiles - 1 && lane == 0) *total_out = excl_tile + total;
+        uint32_t end;
+        const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, end);
+        uint32_t o = base + incl - mine;
+        if (w0 + 3u < nwords) {
+            *reinterpret_cast<uint4*>(word_prefix + w0) = make_uint4(o, o + c[0], o + c[0] + c[1], o + c[0] + c[1] + c[2]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { if (w0 + j < nwords) word_prefix[w0 + j] = o; o += c[j]; }
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) *total_out = end;
     }
 }
 
