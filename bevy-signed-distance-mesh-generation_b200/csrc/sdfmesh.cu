@@ -9,6 +9,7 @@
 // There is no CPU fallback: every compute entry point needs a CUDA device and fails with SDM_ERR_NO_DEVICE /
 // SDM_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,28 @@
 #include <vector>
 
 #include "sdm_kernels.cuh"
+
+// Device-side clears go through a kernel (one engine for everything on the compute stream; the copy engines are left to the
+// asynchronous mesh download).  `bytes` and `p` must be multiples of 4.
+__global__ void __launch_bounds__(256) k_fill32(uint32_t* __restrict__ p, uint32_t value, size_t nwords) {
+    const size_t n4 = nwords >> 2;
+    const uint4 v4 = make_uint4(value, value, value, value);
+    const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+        for (size_t i = tid; i < n4; i += stride) reinterpret_cast<uint4*>(p)[i] = v4;
+        for (size_t i = (n4 << 2) + tid; i < nwords; i += stride) p[i] = value;
+    } else {
+        for (size_t i = tid; i < nwords; i += stride) p[i] = value;
+    }
+}
+static cudaError_t dev_fill(cudaStream_t s, void* p, int byte_value, size_t bytes) {
+    const uint32_t b = (uint32_t) (byte_value & 0xFF), v = b | (b << 8) | (b << 16) | (b << 24);
+    const size_t nwords = bytes >> 2;
+    if (nwords == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned) std::min<size_t>((nwords / 4 + 255) / 256 + 1, 148 * 8);
+    k_fill32<<<blocks, 256, 0, s>>>(reinterpret_cast<uint32_t*>(p), v, nwords);
+    return cudaGetLastError();
+}
 
 static_assert(sizeof(SdmPoint) == 12 && alignof(SdmPoint) == 4, "Point layout (bindings.h:43-47)");
 static_assert(sizeof(SdmVoxelField) == 32 && offsetof(SdmVoxelField, voxels) == 16 && offsetof(SdmVoxelField, voxel_count) == 24,
@@ -208,6 +231,7 @@ struct SdmHandle {
     DevBuf<uint64_t> tiles, tiles2;
     DevBuf<Straggler> stragglers;
     uint32_t cap_stragglers = 0;
+    uint32_t cases_epoch = 0;           // epoch passed to that k_refine (DevState::cases_from_refine)
     int cases_for_level = -1;           // level whose case indices the last k_refine wrote (-1: none)
     uint32_t table1_entries = 0;        // entries of table1 actually used (adaptive: sized from the previous mesh)
     DevBuf<DevState> state;
@@ -320,7 +344,10 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     CK(h->cell_maybe.reserve((size_t) G * G * G));
     fine.maybe = nullptr; coarse.maybe = nullptr;
     k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_coarse.p, coarse, nullptr, 0, rho(coarse.cell), nullptr);
-    k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell), h->cell_maybe.p);
+    if (W <= 32)
+        k_build_masks_fine<<<h->num_sms * 4, 256, 0, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell), h->cell_maybe.p);
+    else
+        k_build_masks<<<h->num_sms * 8, 256, 0, h->stream>>>(h->scene.p, h->masks_fine.p, fine, h->masks_coarse.p, Gc, rho(fine.cell), h->cell_maybe.p);
     fine.maybe = h->cell_maybe.p;
     mark(h, "k_build_masks_x2");
     h->stats.kernel_launches += 2;
@@ -366,10 +393,10 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     const size_t max_tiles = std::max<size_t>(((size_t) h->cap_tris * 3 / 32 + 31) / 32, (size_t) cap_vox / 32) + 64;
     const size_t old_tiles = h->tiles.n;
     CK(h->tiles.reserve(max_tiles));
-    if (h->tiles.n != old_tiles) CK(cudaMemsetAsync(h->tiles.p, 0, h->tiles.n * sizeof(uint64_t), h->stream));
+    if (h->tiles.n != old_tiles) CK(dev_fill(h->stream, h->tiles.p, 0, h->tiles.n * sizeof(uint64_t)));
     const size_t old_tiles2 = h->tiles2.n;
     CK(h->tiles2.reserve((size_t) cap_vox / 32 + 64));
-    if (h->tiles2.n != old_tiles2) CK(cudaMemsetAsync(h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t), h->stream));
+    if (h->tiles2.n != old_tiles2) CK(dev_fill(h->stream, h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t)));
     h->cap_stragglers = h->cap_uniq / 8 + 4096;
     CK(h->stragglers.reserve(h->cap_stragglers));
     h->table1_entries = h->table_entries;
@@ -381,15 +408,15 @@ int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
 uint32_t next_epoch(SdmHandle* h) {
     h->epoch++;
     if (h->epoch >= (1u << 30)) {   // wrap: make every stale descriptor invalid again
-        cudaMemsetAsync(h->tiles.p, 0, h->tiles.n * sizeof(uint64_t), h->stream);
-        cudaMemsetAsync(h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t), h->stream);
+        dev_fill(h->stream, h->tiles.p, 0, h->tiles.n * sizeof(uint64_t));
+        dev_fill(h->stream, h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t));
         h->epoch = 1;
     }
     return h->epoch;
 }
 
 int reset_state(SdmHandle* h) {
-    CK(cudaMemsetAsync(h->state.p, 0, sizeof(DevState), h->stream));
+    CK(dev_fill(h->stream, h->state.p, 0, sizeof(DevState)));
     return SDM_OK;
 }
 
@@ -421,11 +448,9 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     int mrc = ensure_masks_any(h);
     if (mrc) return mrc;
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
-    if (with_cases) cudaMemsetAsync(&h->state.p->cases_from_refine, 0, 4, h->stream);   // the kernel stores 2 if a lattice is inexact
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p,
-                                                                with_cases ? 1 : 0, h->level == 0 && h->grid.enabled ? 1 : 0);
+                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, h->level == 0 && h->grid.enabled ? 1 : 0);
     mark(h, "k_refine");
-    cudaMemsetAsync(&h->state.p->ticket[TK_REFINE_EMIT], 0, 4, h->stream);
     k_refine_emit<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cap_vox,
                                                      ox, oy, oz, h->m27.p, with_cases ? h->cases.p : nullptr);
     h->cases_for_level = with_cases ? h->level + 1 : -1;
@@ -454,16 +479,12 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     const size_t smem = smem_for(h, 256), smem128 = smem_for(h, 128);
     cudaStream_t s = h->stream;
     // the mesh stage may be re-run on the same field: reset the mesh-stage counters and tickets only (not error_flags)
-    CK(cudaMemsetAsync(&h->state.p->n_tris_raw, 0, offsetof(DevState, error_flags) - offsetof(DevState, n_tris_raw), s));
-    CK(cudaMemsetAsync(&h->state.p->ticket[TK_CLASSIFY], 0, sizeof(uint32_t) * (TK_COUNT - TK_CLASSIFY + 1), s));   // + n_stragglers
-    CK(cudaMemsetAsync(&h->state.p->newton_iters, 0, sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(&h->state.p->cull_tiles, 0, 4 * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(&h->state.p->prim_evals[WK_CLASSIFY], 0, 5 * sizeof(unsigned long long), s));   // refine's counter is reset with the field
+    k_reset_mesh_state<<<1, 32, 0, s>>>(h->state.p);
     // vertex de-duplication table: sized from the previous mesh of this handle (4x its vertex count), full size at first;
     // an overflow is detected (ERR_HASH_FULL) and retried with the full table
-    CK(cudaMemsetAsync(h->table1.p, 0xFF, (size_t) h->table1_entries * 16, s));
+    CK(dev_fill(s, h->table1.p, 0xFF, (size_t) h->table1_entries * 16));
     mark(h, "clears");
-    k_cases<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, h->cases.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? 1 : 0);
+    k_cases<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, h->cases.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? h->cases_epoch : 0u);
     k_tri_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->cases.p, h->tri_off.p, next_epoch(h), h->tiles.p, h->cap_tris);
     mark(h, "k_cases+k_tri_offsets");
     k_edges<<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->won.p, sx, sy, sz);
@@ -648,7 +669,7 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         memset(h->host_range, 0, 16);
         if (h->shard_range.reserve(4) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc range"); break; }
         if (h->state.reserve(1) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc state"); break; }
-        cudaMemsetAsync(h->state.p, 0, sizeof(DevState), h->stream);
+        dev_fill(h->stream, h->state.p, 0, sizeof(DevState));
         cudaMemcpyToSymbolAsync(c_mc_packed, SDM_MC_PACKED_INIT, sizeof(SDM_MC_PACKED_INIT), 0, cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyToSymbolAsync(c_mc_edgemask, SDM_MC_EDGEMASK_INIT, sizeof(SDM_MC_EDGEMASK_INIT), 0, cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyToSymbolAsync(c_mc_ntri, SDM_MC_NTRI_INIT, sizeof(SDM_MC_NTRI_INIT), 0, cudaMemcpyHostToDevice, h->stream);
@@ -857,7 +878,7 @@ static int run_mesh(SdmHandle* h, SdmMesh* out_mesh, bool timed) {
             return SDM_OK;
         }
         if (only_table1_overflow(h, flags)) {
-            CK(cudaMemsetAsync(&h->state.p->error_flags, 0, 4, h->stream));
+            CK(dev_fill(h->stream, &h->state.p->error_flags, 0, 4));
             continue;
         }
         // a mesh-stage capacity was exceeded: keep the field (download / grow / upload) and retry
@@ -918,7 +939,12 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
     uint32_t want = h->cap_vox;
     const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
     while (want < n0) want = grown(want);
+    static const bool trace = getenv("SDM_TRACE") != nullptr;   // developer switch: host-side phase times of sdm_remesh on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    if (getenv("SDM_REMESH_PRESYNC")) CK(cudaStreamSynchronize(h->stream));   // experiment: see tools/e2e_probe.py
     for (int attempt = 0; attempt < 10; attempt++) {
+        const auto t_begin = now();
         rc = ensure_capacity(h, want);
         if (rc) return rc;
         prof_begin(h);
@@ -935,12 +961,14 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
         rc = enqueue_mesh(h);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev1, h->stream));
+        const double t_enqueue = ms_since(t_begin);
         uint32_t flags = 0;
         rc = fetch_state(h, &flags);
         if (rc) return rc;
         if (!flags) {
             float ms = 0;
             cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            if (trace) fprintf(stderr, "sdm_remesh: enqueue %.3f ms, total %.3f ms, gpu %.3f ms\n", t_enqueue, ms_since(t_begin), ms);
             h->stats.last_gpu_ms = ms;
             h->mesh_valid = true;
             fill_stats(h, true);
@@ -979,6 +1007,7 @@ int sdm_mesh_download_async(SdmHandle* h, const SdmMesh* m, float* positions, fl
     if (m->vertex_count && normals) CK(cudaMemcpyAsync(normals, m->normals, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, cs));
     if (m->triangle_count && indices) CK(cudaMemcpyAsync(indices, m->indices, (size_t) m->triangle_count * 12, cudaMemcpyDeviceToHost, cs));
     CK(cudaEventRecord(h->ev_copy_done[b], cs));
+    (void) cudaStreamQuery(cs);   // push the copies to the device now: kernels enqueued right behind them must not start first
     return SDM_OK;
 }
 int sdm_mesh_download_wait(SdmHandle* h) {
@@ -1045,7 +1074,12 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
     uint32_t want = h->cap_vox;
     const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
     while (want < n0) want = grown(want);
+    static const bool trace = getenv("SDM_TRACE") != nullptr;   // developer switch: host-side phase times of sdm_remesh on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    if (getenv("SDM_REMESH_PRESYNC")) CK(cudaStreamSynchronize(h->stream));   // experiment: see tools/e2e_probe.py
     for (int attempt = 0; attempt < 10; attempt++) {
+        const auto t_begin = now();
         rc = ensure_capacity(h, want);
         if (rc) return rc;
         prof_begin(h);
@@ -1201,7 +1235,7 @@ int sdm_selftest_math(SdmHandle* h, unsigned long long div_samples, unsigned lon
     CK(cudaSetDevice(h->device));
     unsigned long long* d = nullptr;
     CK(cudaMalloc(&d, 32));
-    CK(cudaMemsetAsync(d, 0, 32, h->stream));
+    CK(dev_fill(h->stream, d, 0, 32));
     k_selftest_math<<<h->num_sms * 8, 256, 0, h->stream>>>(d, div_samples);
     h->stats.kernel_launches++;
     CK(cudaGetLastError());

@@ -31,7 +31,7 @@ for rep in range(2):
     t = time.perf_counter(); hp.copy_(d, non_blocking=True); torch.cuda.synchronize(); dt = time.perf_counter() - t
     print(f"torch D2H pinned: {dt*1e3:.2f} ms  {nbytes/dt/1e9:.1f} GB/s")
 # 2. loops
-def loop(n, with_scene, with_dl, tag):
+def loop(n, with_scene, with_dl, tag, nap=0.0):
     h.download_wait(); torch.cuda.synchronize()
     ph = np.zeros(3)
     t0 = time.perf_counter()
@@ -42,6 +42,7 @@ def loop(n, with_scene, with_dl, tag):
         mm = h.remesh(bb, init, levels, download=False)
         c = time.perf_counter()
         if with_dl: h.download_into_async(mm, *(x.data_ptr() for x in bufs[i & 1]))
+        if nap: time.sleep(nap)
         e = time.perf_counter()
         ph += [b - a, c - b, e - c]
     h.download_wait()
@@ -50,5 +51,6 @@ def loop(n, with_scene, with_dl, tag):
 loop(10, False, False, "remesh only")
 loop(10, True, False, "set_scene + remesh")
 loop(10, False, True, "remesh + async download")
+loop(10, False, True, "remesh + async download + 0.3 ms nap", nap=0.0003)
 loop(10, True, True, "full e2e")
 loop(10, True, True, "full e2e (again)")
