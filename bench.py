@@ -322,7 +322,7 @@ def main():
     if rank == 0:
         line = {
             "metric": metric, "value": float(res) ** 3 * args.steps / elapsed, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic procedural scene (analytic SDF); no dataset",
             "config": dict(config, l2="every step clears >0.5 GB of hash tables and rewrites all intermediates (working set > 126 MB L2); no separate flush",
                            parallelism=f"x-slab shards of the level-{runner.split_level} active list over {world} GPU(s), mesh shards gathered to rank 0 (NCCL)" if world > 1 else "1 GPU"),
