@@ -942,7 +942,6 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
     static const bool trace = getenv("SDM_TRACE") != nullptr;   // developer switch: host-side phase times of sdm_remesh on stderr
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
-    if (getenv("SDM_REMESH_PRESYNC")) CK(cudaStreamSynchronize(h->stream));   // experiment: see tools/e2e_probe.py
     for (int attempt = 0; attempt < 10; attempt++) {
         const auto t_begin = now();
         rc = ensure_capacity(h, want);
@@ -1074,12 +1073,7 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
     uint32_t want = h->cap_vox;
     const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
     while (want < n0) want = grown(want);
-    static const bool trace = getenv("SDM_TRACE") != nullptr;   // developer switch: host-side phase times of sdm_remesh on stderr
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
-    if (getenv("SDM_REMESH_PRESYNC")) CK(cudaStreamSynchronize(h->stream));   // experiment: see tools/e2e_probe.py
     for (int attempt = 0; attempt < 10; attempt++) {
-        const auto t_begin = now();
         rc = ensure_capacity(h, want);
         if (rc) return rc;
         prof_begin(h);
