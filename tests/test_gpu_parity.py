@@ -188,3 +188,27 @@ def test_async_download_overlaps_and_matches(handler):
         for pos, nrm, idx in lst:
             assert np.array_equal(idx.numpy().view(np.uint32), want[lv].indices)
             assert np.array_equal(bits(pos.numpy()), bits(want[lv].positions)) and np.array_equal(bits(nrm.numpy()), bits(want[lv].normals))
+
+
+@pytest.mark.parametrize("case,init,levels", [("sd_obj_init64_l3", 64, 3), ("sd_obj_init32_l5", 32, 5)])
+def test_fullsize_matches_reference_goldens(handler, oracle_mod, case, init, levels):
+    """BASELINE's full sizes: sd_obj at 512^3 (configs[1]) and at 1024^3.  The expected values come from the reference's own
+    kernels compiled for the host (tools/gen_golden_fullsize.py -> tests/golden/golden_fullsize.json): active-list length
+    and bytes at every level, triangle / vertex counts, index buffer, positions and normals, all by FNV-1a-64 of the raw bytes."""
+    import json
+    import pathlib
+
+    want = json.loads((pathlib.Path(__file__).parent / "golden" / "golden_fullsize.json").read_text())["cases"][case]
+    h = lambda a: "%016x" % oracle_mod.fnv1a64(np.ascontiguousarray(a))
+    handler.set_scene(scenes.sd_obj())
+    handler.field_reset(5.0, init)
+    assert h(handler.field_download()) == want["fnv_voxels_per_level"][0]
+    for lvl in range(levels):
+        assert handler.field_refine() == want["level_counts"][lvl + 1]
+        assert h(handler.field_download()) == want["fnv_voxels_per_level"][lvl + 1], f"active list of level {lvl + 1} differs"
+    mesh = handler.remesh(5.0, init, levels)
+    assert handler.stats()["level_counts"][: levels + 1] == want["level_counts"]
+    assert (mesh.triangle_count, mesh.vertex_count) == (want["triangles"], want["vertices"])
+    assert h(mesh.indices) == want["fnv_indices"], "index topology differs"
+    assert h(mesh.positions) == want["fnv_positions"], "vertex positions differ"
+    assert h(mesh.normals) == want["fnv_normals"], "vertex normals differ"
