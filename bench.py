@@ -188,6 +188,16 @@ def cpu_sampled_remesh(scene_name, scene, bb, init, levels, res, budget_s=15.0, 
     }
 
 
+def ncu_traffic(workload, kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum per remesh of the given kernels, from the committed `ncu --set full` capture of
+    this workload (profiles/ncu_traffic.json, see its _doc); None if that workload was not captured."""
+    try:
+        t = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(workload)
+        return float(sum(t[k]["dram_bytes_read"] + t[k]["dram_bytes_write"] for k in kernels)) if t else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -299,7 +309,7 @@ def main():
         work = pe[stage_of[top]]
         ach = work * ops_pp / (kavg[top] * 1e-3) / 1e12
         roofline = {"kernel": top, "bound": "fp32", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                    "frac": ach / fp32_peak_tflops, "traffic": None,
+                    "frac": ach / fp32_peak_tflops, "traffic": ncu_traffic(args.workload, [top]),
                     "peak_source": f"148 SM x 128 FP32 lanes x {sm_max_mhz:.0f} MHz, one op per lane-cycle (no FMA: -fmad=false is part of the parity contract)",
                     "algorithmic_ops_per_prim_point": ops_pp, "prim_point_evals_per_launch": work, "avg_launch_ms": kavg[top],
                     "share_of_step": kavg[top] / step_sum}
@@ -309,7 +319,8 @@ def main():
         if "k_emit_vertices" in kavg and "k_emit_indices" in kavg:
             t_emit = (kavg["k_emit_vertices"] + kavg["k_emit_indices"]) * 1e-3
             roofline_hbm = {"kernel": "k_emit_vertices+k_emit_indices", "bound": "hbm", "achieved": emit_bytes / t_emit / 1e9, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": emit_bytes / t_emit / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                            "unit": "GB/s", "frac": emit_bytes / t_emit / 1e9 / hbm_peak, "traffic": ncu_traffic(args.workload, ["k_emit_vertices", "k_emit_indices"]),
+                            "peak_source": peak_src,
                             "algorithmic_bytes": emit_bytes}
 
     # ---- end-to-end arm: host scene in, pinned host mesh out, every step ------------------------------------------
