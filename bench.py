@@ -238,6 +238,7 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")   # the gather is point-to-point: 421 -> 492 GB/s into rank 0 (tools/p2p_probe.py)
         import torch.distributed as dist_mod
 
         dist = dist_mod
@@ -346,7 +347,8 @@ def main():
             "roofline": roofline, "roofline_hbm": roofline_hbm,
         }
         if world > 1:
-            line["rank0_phase_ms"] = dict(zip(("local_shard", "count_allgather", "gather", "weld"), getattr(runner, "last_phases", [])))
+            line["rank0_phase_ms"] = dict(zip(("local_shard_and_weld", "counts_ranges_boundary_keys", "resolve", "gather"), getattr(runner, "last_phases", [])))
+            line["root_weld_fallback"] = bool(getattr(runner, "last_fallback", False))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sampled_remesh(scene_name, scene, bb, init, levels, res)
         print(json.dumps(line), flush=True)

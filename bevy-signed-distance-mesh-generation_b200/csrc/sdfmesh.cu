@@ -238,6 +238,11 @@ struct SdmHandle {
     DevState* host_state = nullptr;   // pinned
     DevBuf<uint32_t> shard_range;     // {lo, hi, n} of the last k_take_shard
     uint32_t* host_range = nullptr;   // pinned
+    uint32_t shard_index = 0;
+    int welded_set = 0, welded_vset = 0;   // output sets holding the local weld's indices / vertices
+    uint32_t welded_v = 0, welded_t = 0;   // rows of the local weld (after sdm_shard_apply_remap: kept vertices)
+    DevBuf<uint32_t> shard_scratch;   // 128 words: x range, counters, per-shard duplicate counts / cursors / offsets
+    uint32_t* host_scratch = nullptr; // pinned mirror
     uint32_t own_tris = 0, own_uniq = 0;   // the local shard's counts (sdm_shard_remesh)
     uint32_t epoch = 1;
     bool mesh_valid = false;
@@ -699,6 +704,8 @@ void sdm_destroy(SdmHandle* h) {
     h->won.release(); h->entry_uid.release(); h->vidx.release(); h->uid_base.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
+    if (h->host_scratch) cudaFreeHost(h->host_scratch);
+    h->shard_scratch.release();
     h->shard_range.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1097,7 +1104,7 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
             rc = enqueue_refine(h, l + 1 == p.levels);
             if (rc) return rc;
         }
-        rc = enqueue_mesh_local(h, false);
+        rc = enqueue_mesh_local(h, true);   // weld keys too: sdm_shard_local_weld follows (the root-weld fallback re-inserts)
         if (rc) return rc;
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaMemcpyAsync(h->host_range, h->shard_range.p, 12, cudaMemcpyDeviceToHost, h->stream));
@@ -1114,6 +1121,7 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
             h->own_tris = h->host_state->n_tris_raw;
             h->own_uniq = h->host_state->n_uniq;
             adapt_table1(h);
+            h->shard_index = shard_index;
             out_info->shard_index = shard_index; out_info->shard_count = shard_count; out_info->split_level = split_level;
             out_info->voxel_begin = h->host_range[0]; out_info->voxel_end = h->host_range[1]; out_info->split_total = h->host_range[2];
             out_info->final_voxels = h->host_state->level_count[h->level];
@@ -1169,6 +1177,197 @@ int sdm_shard_reserve(SdmHandle* h, uint32_t total_vertices, uint32_t total_tria
     }
     cudaFree(old_pos); cudaFree(old_nrm); cudaFree(old_uid); cudaFree(old_bits);
     return rc;
+}
+
+static int ensure_shard_scratch(SdmHandle* h) {
+    CK(h->shard_scratch.reserve(128));
+    if (!h->host_scratch) CK(cudaMallocHost(&h->host_scratch, 128 * sizeof(uint32_t)));
+    return SDM_OK;
+}
+static float ord_to_float(uint32_t o) { const int32_t i = (int32_t) o; const int32_t b = i ^ ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &b, 4); return f; }
+
+int sdm_shard_local_weld(SdmHandle* h, SdmShardWeld* out) {
+    if (!h || !out) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_shard_scratch(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CK(cudaEventRecord(h->ev0, s));
+    const int b = h->out_sel;
+    rc = enqueue_weld(h, true);
+    if (rc) return rc;
+    k_shard_scratch_init<<<1, 32, 0, s>>>(h->shard_scratch.p);
+    k_shard_xrange<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[b].p, h->shard_scratch.p);
+    h->stats.kernel_launches += 2;
+    CK(cudaEventRecord(h->ev1, s));
+    CK(cudaMemcpyAsync(h->host_scratch, h->shard_scratch.p, 16, cudaMemcpyDeviceToHost, s));
+    uint32_t flags = 0;
+    rc = fetch_state(h, &flags);
+    if (rc) return rc;
+    if (flags) return fail(SDM_ERR_CAPACITY, "weld table overflow");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_gpu_ms = ms;
+    h->welded_set = b; h->welded_vset = b;
+    h->out_sel ^= 1;   // like mesh_view: the next weld writes the other set
+    h->welded_v = h->host_state->n_verts_out; h->welded_t = h->host_state->n_tris_out;
+    out->vertices = h->welded_v;
+    out->triangles = h->welded_t;
+    out->nonfinite = h->host_scratch[2] + (h->welded_v >= (1u << 24) ? 1u : 0u);   // 24-bit local indices in the key rows
+    out->min_x = ord_to_float(h->host_scratch[0]);
+    out->max_x = ord_to_float(h->host_scratch[1]);
+    if (h->host_scratch[0] == 0x7fffffffu) { out->min_x = 1.0f; out->max_x = 0.0f; }
+    return SDM_OK;
+}
+
+int sdm_shard_boundary_keys(SdmHandle* h, const float* lo, const float* hi, uint32_t interval_count, uint32_t** out_rows_device, uint32_t* out_count) {
+    if (!h || !out_rows_device || !out_count || (interval_count && (!lo || !hi))) return fail(SDM_ERR_INVALID, "null argument");
+    if (interval_count > 32) return fail(SDM_ERR_INVALID, "at most 32 intervals");
+    if (h->shard_index > 255) return fail(SDM_ERR_INVALID, "at most 256 shards");
+    CK(cudaSetDevice(h->device));
+    ShardIntervals iv {};
+    iv.count = interval_count;
+    for (uint32_t i = 0; i < interval_count; i++) { iv.lo[i] = lo[i]; iv.hi[i] = hi[i]; }
+    cudaStream_t s = h->stream;
+    const uint32_t cap_rows = h->table_entries;   // the vertex table is free after k_orient: its 16-byte entries hold the rows
+    k_shard_boundary_keys<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[h->welded_vset].p, iv, h->shard_index, h->table1.p, cap_rows, h->shard_scratch.p);
+    h->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(h->host_scratch, h->shard_scratch.p, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->host_scratch[3] > cap_rows) return fail(SDM_ERR_CAPACITY, "too many boundary candidates");
+    *out_rows_device = reinterpret_cast<uint32_t*>(h->table1.p);
+    *out_count = h->host_scratch[3];
+    return SDM_OK;
+}
+
+int sdm_shard_key_scratch(SdmHandle* h, uint32_t rows, uint32_t** out_rows_device) {
+    if (!h || !out_rows_device) return fail(SDM_ERR_INVALID, "null argument");
+    if (rows > h->table_entries) return fail(SDM_ERR_CAPACITY, "too many boundary candidates");
+    *out_rows_device = reinterpret_cast<uint32_t*>(h->table1.p);
+    return SDM_OK;
+}
+
+int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total, const uint32_t* vertex_counts, uint32_t shards,
+                      uint32_t* out_removed, uint32_t* out_goff, uint32_t** out_pairs_device, uint32_t* out_failed) {
+    if (!h || !vertex_counts || !out_removed || !out_goff || !out_pairs_device || !out_failed || (total && !rows_device))
+        return fail(SDM_ERR_INVALID, "null argument");
+    if (shards == 0 || shards > 32) return fail(SDM_ERR_INVALID, "1..32 shards");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_shard_scratch(h);
+    if (rc) return rc;
+    ShardOffsets so {};
+    so.count = shards;
+    uint64_t vsum = 0;
+    for (uint32_t s = 0; s < shards; s++) { so.voff[s] = (uint32_t) vsum; vsum += vertex_counts[s]; }
+    so.voff[shards] = (uint32_t) vsum;
+    *out_failed = 0;
+    *out_pairs_device = reinterpret_cast<uint32_t*>(h->slot_ref.p);
+    const uint32_t nwords = (uint32_t) (vsum / 32 + 2);
+    const uint32_t entries = std::min<uint32_t>(pow2_at_least(std::max<uint64_t>((uint64_t) total * 2, 1024)), h->table_entries);
+    if (vsum >= (1ull << 32) || nwords > h->first_bits.n || nwords > h->first_prefix.n || total > h->wref.n || (uint64_t) total * 2 > h->slot_ref.n ||
+        (uint64_t) entries * 4 < (uint64_t) total * 5) {
+        *out_failed = 1;   // does not fit the root's scratch: the caller falls back to the root weld
+        return SDM_OK;
+    }
+    cudaStream_t st = h->stream;
+    uint32_t* sc = h->shard_scratch.p;   // [32..64) duplicates per shard, [64..96) cursors, [96..128) global offsets, [4] errors
+    CK(dev_fill(st, sc, 0, 128 * 4));
+    CK(dev_fill(st, h->first_bits.p, 0, (size_t) nwords * 4));
+    if (total) {
+        CK(dev_fill(st, h->table2.p, 0xFF, (size_t) entries * 16));
+        const uint4* rows = reinterpret_cast<const uint4*>(rows_device);
+        k_res_insert<<<h->g_light, 256, 0, st>>>(rows, total, h->table2.p, entries - 1, h->wref.p, sc + 4);
+        k_res_mark<<<h->g_light, 256, 0, st>>>(rows, total, h->table2.p, h->wref.p, so, h->first_bits.p, sc + 32);
+    }
+    k_scan_bits_1block<<<1, 1024, 0, st>>>(h->first_bits.p, h->first_prefix.p, nwords);
+    CK(cudaMemcpyAsync(h->host_scratch, sc, 128 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->host_scratch[4]) { *out_failed = 1; return SDM_OK; }
+    uint32_t psum = 0;
+    for (uint32_t s = 0; s < shards; s++) { out_removed[s] = h->host_scratch[32 + s]; so.poff[s] = psum; psum += out_removed[s]; }
+    so.poff[shards] = psum;
+    k_res_pairs<<<h->g_light, 256, 0, st>>>(reinterpret_cast<const uint4*>(rows_device), total, h->table2.p, h->wref.p, so, h->first_bits.p, h->first_prefix.p,
+                                            sc + 64, reinterpret_cast<uint2*>(h->slot_ref.p), sc + 96);
+    h->stats.kernel_launches += 7;
+    CK(cudaMemcpyAsync(h->host_scratch, sc, 128 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t s = 0; s < shards; s++) out_goff[s] = h->host_scratch[96 + s];
+    return SDM_OK;
+}
+
+int sdm_shard_pair_scratch(SdmHandle* h, uint32_t pairs, uint32_t** out_pairs_device) {
+    if (!h || !out_pairs_device) return fail(SDM_ERR_INVALID, "null argument");
+    if ((uint64_t) pairs * 2 > h->slot_ref.n) return fail(SDM_ERR_CAPACITY, "too many duplicate pairs");
+    *out_pairs_device = reinterpret_cast<uint32_t*>(h->slot_ref.p);
+    return SDM_OK;
+}
+
+int sdm_shard_apply_remap(SdmHandle* h, const uint32_t* pairs_device, uint32_t npairs, uint32_t global_offset) {
+    if (!h || (npairs && !pairs_device)) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const uint32_t V = h->welded_v;
+    const uint32_t nwords = V / 32 + 2;
+    if (nwords > h->first_bits.n || nwords > h->first_prefix.n || V > h->vidx.n) return fail(SDM_ERR_CAPACITY, "remap scratch too small");
+    const int b = h->welded_set, vb = b ^ 1;
+    CK(dev_fill(st, h->first_bits.p, 0, (size_t) nwords * 4));
+    if (npairs) k_remap_mark<<<h->g_light, 256, 0, st>>>(reinterpret_cast<const uint2*>(pairs_device), npairs, h->first_bits.p, h->vidx.p);
+    k_scan_bits_1block<<<1, 1024, 0, st>>>(h->first_bits.p, h->first_prefix.p, nwords);
+    k_remap_apply<<<h->g_light, 256, 0, st>>>(h->state.p, h->first_bits.p, h->first_prefix.p, h->vidx.p, global_offset, h->out_pos[b].p, h->out_nrm[b].p,
+                                              h->out_pos[vb].p, h->out_nrm[vb].p, h->out_idx[b].p);
+    h->stats.kernel_launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));   // the buffers are handed to NCCL on another stream next
+    h->welded_vset = vb;
+    h->welded_v = V - npairs;
+    return SDM_OK;
+}
+
+int sdm_shard_welded_buffers(SdmHandle* h, SdmShardBuffers* out) {
+    if (!h || !out) return fail(SDM_ERR_INVALID, "null argument");
+    out->positions = h->out_pos[h->welded_vset].p; out->normals = h->out_nrm[h->welded_vset].p; out->triangle_vertex_ids = h->out_idx[h->welded_set].p;
+    out->capacity_vertices = h->cap_uniq; out->capacity_triangles = h->cap_tris;
+    return SDM_OK;
+}
+
+int sdm_shard_reserve_welded(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    if (total_vertices <= h->cap_uniq && total_triangles <= h->cap_tris) return SDM_OK;
+    uint32_t want = h->cap_vox;
+    while ((uint64_t) want * 2 < total_vertices || (uint64_t) want * 3 < total_triangles) {
+        const uint32_t g = grown(want);
+        if (g == want) return fail(SDM_ERR_CAPACITY, "merged mesh too large");
+        want = g;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
+    // keep the local welded rows: detach them, re-allocate everything, copy back
+    const int b = h->welded_set, vb = h->welded_vset;
+    float* old_pos = h->out_pos[vb].p; float* old_nrm = h->out_nrm[vb].p; uint32_t* old_idx = h->out_idx[b].p;
+    h->out_pos[vb].p = nullptr; h->out_pos[vb].n = 0; h->out_nrm[vb].p = nullptr; h->out_nrm[vb].n = 0; h->out_idx[b].p = nullptr; h->out_idx[b].n = 0;
+    int rc = ensure_capacity(h, want);
+    if (rc == SDM_OK) {
+        cudaMemcpyAsync(h->out_pos[vb].p, old_pos, (size_t) h->welded_v * 12, cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->out_nrm[vb].p, old_nrm, (size_t) h->welded_v * 12, cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->out_idx[b].p, old_idx, (size_t) h->welded_t * 12, cudaMemcpyDeviceToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(old_pos); cudaFree(old_nrm); cudaFree(old_idx);
+    return rc;
+}
+
+int sdm_shard_finish(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh) {
+    if (!h || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
+    if (total_vertices > h->cap_uniq || total_triangles > h->cap_tris) return fail(SDM_ERR_CAPACITY, "call sdm_shard_reserve_welded first");
+    CK(cudaSetDevice(h->device));
+    const int b = h->welded_set;
+    CK(cudaEventRecord(h->ev_mesh_done[b], h->stream));   // the received rows were written on other streams: callers synchronise first
+    out_mesh->positions = h->out_pos[h->welded_vset].p; out_mesh->normals = h->out_nrm[h->welded_vset].p; out_mesh->indices = h->out_idx[b].p;
+    out_mesh->vertex_count = total_vertices; out_mesh->triangle_count = total_triangles;
+    out_mesh->on_device = 1; out_mesh->reserved = b;
+    h->stats.last_gpu_ms = 0.0f;
+    return SDM_OK;
 }
 
 int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh) {

@@ -1017,6 +1017,132 @@ __global__ void __launch_bounds__(256) k_first_slot_merged(DevState* st, uint32_
     }
 }
 
+// ---- distributed weld: local weld per shard, boundary keys resolved on rank 0, concatenation -------
+// Shards DO share vertices: every edge of the interface layer is meshed by both neighbours, and any two vertices with the
+// same quantised key are one vertex in the reference's weld (src/cuda/mod.rs:270-277).  Global first-occurrence order is
+// shard-major (the triangle lists are concatenated in shard order), so a key's owner is its copy in the LOWEST shard, at
+// that shard's local position; every other copy is removed from its shard and its index re-mapped to the owner.  With the
+// welded local lists concatenated (offset Voff[s] = vertices of the shards before s), a kept vertex's global id is its
+// concatenated position minus the number of removed vertices before it - one prefix pop-count over a removal bitmap.
+// scratch words: [0] min ordered x, [1] max ordered x, [2] non-finite vertices, [3] boundary candidates
+__global__ void k_shard_scratch_init(uint32_t* scratch) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { scratch[0] = 0x7fffffffu; scratch[1] = 0x80000000u; scratch[2] = 0; scratch[3] = 0; }
+}
+__global__ void __launch_bounds__(256) k_shard_xrange(DevState* st, const float* __restrict__ out_pos, uint32_t* scratch) {
+    const uint32_t n = st->n_verts_out;
+    int lo = 0x7fffffff, hi = (int) 0x80000000;
+    uint32_t bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = out_pos[3 * (size_t) i], y = out_pos[3 * (size_t) i + 1], z = out_pos[3 * (size_t) i + 2];
+        if (fabsf(x) <= FLT_MAX && fabsf(y) <= FLT_MAX && fabsf(z) <= FLT_MAX) { lo = min(lo, f2ord(x)); hi = max(hi, f2ord(x)); }
+        else bad++;
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi); bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31u) == 0) {
+        atomicMin(reinterpret_cast<int*>(scratch), lo); atomicMax(reinterpret_cast<int*>(scratch) + 1, hi);
+        if (bad) atomicAdd(scratch + 2, bad);
+    }
+}
+// A vertex of this shard can share its key with a vertex of another shard only if its x lies within that shard's x range
+// (equal keys: |x1 - x2| < 1.1e-5; the intervals handed in are widened by 1e-4).  Rows: kx, ky, kz, shard << 24 | local index.
+struct ShardIntervals { float lo[32], hi[32]; uint32_t count; };
+__global__ void __launch_bounds__(256) k_shard_boundary_keys(DevState* st, const float* __restrict__ out_pos, ShardIntervals iv, uint32_t shard,
+                                                             uint4* __restrict__ out_rows, uint32_t cap_rows, uint32_t* scratch) {
+    const uint32_t n = st->n_verts_out;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = out_pos[3 * (size_t) i];
+        bool cand = false;
+        for (uint32_t q = 0; q < iv.count; q++) cand = cand || (x >= iv.lo[q] && x <= iv.hi[q]);
+        if (!cand) continue;
+        const uint32_t slot = atomicAdd(scratch + 3, 1u);
+        if (slot < cap_rows)
+            out_rows[slot] = make_uint4(weld_key_component(x), weld_key_component(out_pos[3 * (size_t) i + 1]), weld_key_component(out_pos[3 * (size_t) i + 2]),
+                                        (shard << 24) | i);
+    }
+}
+struct ShardOffsets { uint32_t voff[33]; uint32_t poff[33]; uint32_t count; };   // vertices / duplicate pairs before each shard
+// rank 0, pass 1: every row enters the key table; the entry keeps the smallest (shard, index) = the key's owner
+__global__ void __launch_bounds__(256) k_res_insert(const uint4* __restrict__ rows, uint32_t total, uint4* table, uint32_t table_mask, uint32_t* __restrict__ rref,
+                                                    uint32_t* err) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint4 r = rows[i];
+        bool won;
+        const uint32_t pos = hash_find_or_insert(table, table_mask, r.x, r.y, r.z, r.w, &won);
+        rref[i] = pos;
+        if (pos == 0xFFFFFFFFu) { atomicAdd(err, 1u); continue; }
+        if (!won) atomicMin(reinterpret_cast<uint32_t*>(table + pos) + 3, r.w);
+    }
+}
+// pass 2: a row that is not its key's owner is a duplicate: mark it in the removal bitmap (concatenated vertex space), count it
+__global__ void __launch_bounds__(256) k_res_mark(const uint4* __restrict__ rows, uint32_t total, const uint4* __restrict__ table, const uint32_t* __restrict__ rref,
+                                                  ShardOffsets so, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ dups /* [shards] */) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t me = rows[i].w, pos = rref[i];
+        if (pos == 0xFFFFFFFFu) continue;
+        if (reinterpret_cast<const uint32_t*>(table + pos)[3] == me) continue;
+        const uint32_t s = me >> 24, c = so.voff[s] + (me & 0xFFFFFFu);
+        atomicOr(bitmap + (c >> 5), 1u << (c & 31u));
+        atomicAdd(dups + s, 1u);
+    }
+}
+// single-block exclusive prefix pop-count (the bitmaps here are ~1 MB)
+__global__ void __launch_bounds__(1024) k_scan_bits_1block(const uint32_t* __restrict__ bits, uint32_t* __restrict__ word_prefix, uint32_t nwords) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (nwords + 1023u) / 1024u, w0 = threadIdx.x * per, w1 = min(w0 + per, nwords);
+    uint32_t sum = 0;
+    for (uint32_t w = w0; w < w1; w++) sum += __popc(bits[w]);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint32_t w = w0; w < w1; w++) { word_prefix[w] = run; run += __popc(bits[w]); }
+}
+// pass 3: (local index, global id of the owner) for every duplicate, grouped by shard; global offset of every shard
+__global__ void __launch_bounds__(256) k_res_pairs(const uint4* __restrict__ rows, uint32_t total, const uint4* __restrict__ table, const uint32_t* __restrict__ rref,
+                                                   ShardOffsets so, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                                                   uint32_t* __restrict__ cursor /* [shards], zeroed */, uint2* __restrict__ pairs, uint32_t* __restrict__ goff /* [shards] */) {
+    if (blockIdx.x == 0 && threadIdx.x < so.count) goff[threadIdx.x] = so.voff[threadIdx.x] - bit_rank(bitmap, prefix, so.voff[threadIdx.x]);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t me = rows[i].w, pos = rref[i];
+        if (pos == 0xFFFFFFFFu) continue;
+        const uint32_t owner = reinterpret_cast<const uint32_t*>(table + pos)[3];
+        if (owner == me) continue;
+        const uint32_t s = me >> 24, oc = so.voff[owner >> 24] + (owner & 0xFFFFFFu);
+        const uint32_t slot = so.poff[s] + atomicAdd(cursor + s, 1u);
+        pairs[slot] = make_uint2(me & 0xFFFFFFu, oc - bit_rank(bitmap, prefix, oc));   // the owner itself is never removed
+    }
+}
+// every rank: removal bitmap and owner ids of its own duplicates
+__global__ void __launch_bounds__(256) k_remap_mark(const uint2* __restrict__ pairs, uint32_t npairs, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ remap) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const uint2 p = pairs[i];
+        atomicOr(bitmap + (p.x >> 5), 1u << (p.x & 31u));
+        remap[p.x] = p.y;
+    }
+}
+// kept vertices move up (stable), indices become global
+__global__ void __launch_bounds__(256) k_remap_apply(DevState* st, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ remap,
+                                                     uint32_t goff, const float* __restrict__ in_pos, const float* __restrict__ in_nrm, float* __restrict__ out_pos,
+                                                     float* __restrict__ out_nrm, uint32_t* __restrict__ idx) {
+    const uint32_t V = st->n_verts_out, n3 = 3u * st->n_tris_out;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < V; i += stride) {
+        if ((bitmap[i >> 5] >> (i & 31u)) & 1u) continue;
+        const uint32_t o = i - bit_rank(bitmap, prefix, i);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { out_pos[3 * (size_t) o + c] = in_pos[3 * (size_t) i + c]; out_nrm[3 * (size_t) o + c] = in_nrm[3 * (size_t) i + c]; }
+    }
+    for (uint32_t j = tid; j < n3; j += stride) {
+        const uint32_t i = idx[j];
+        idx[j] = ((bitmap[i >> 5] >> (i & 31u)) & 1u) ? remap[i] : goff + i - bit_rank(bitmap, prefix, i);
+    }
+}
+
 // ---- test / probe kernels -------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_eval_sdf(const uint4* __restrict__ scene, const float* __restrict__ pts, uint32_t n, float* __restrict__ out,
                                                   MaskGrid grid) {

@@ -67,6 +67,11 @@ class _ShardInfo(ctypes.Structure):
                                                "final_voxels", "unique_vertices", "raw_triangles")]
 
 
+class _ShardWeld(ctypes.Structure):
+    _fields_ = [("vertices", ctypes.c_uint32), ("triangles", ctypes.c_uint32), ("nonfinite", ctypes.c_uint32),
+                ("min_x", ctypes.c_float), ("max_x", ctypes.c_float)]
+
+
 class _ShardBuffers(ctypes.Structure):
     _fields_ = [("positions", ctypes.c_void_p), ("normals", ctypes.c_void_p), ("triangle_vertex_ids", ctypes.c_void_p),
                 ("capacity_vertices", ctypes.c_uint32), ("capacity_triangles", ctypes.c_uint32)]
@@ -81,6 +86,8 @@ ABI_SYMBOLS = [
     "sdm_voxel_field_to_mesh", "sdm_mesh_free", "sdm_field_reset", "sdm_field_upload", "sdm_field_refine", "sdm_field_count",
     "sdm_field_download", "sdm_field_cases", "sdm_field_to_mesh", "sdm_remesh", "sdm_mesh_download", "sdm_field_triangle_soup",
     "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
+    "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_pair_scratch",
+    "sdm_shard_apply_remap", "sdm_shard_welded_buffers", "sdm_shard_reserve_welded", "sdm_shard_finish",
     "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
 
@@ -348,6 +355,56 @@ class CudaHandler:
     def shard_weld(self, total_vertices: int, total_triangles: int, download: bool = False):
         m = _Mesh()
         self._check(self._lib.sdm_shard_weld(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles), ctypes.byref(m)))
+        return self._download(m) if download else m
+
+    # distributed weld: local weld, boundary keys resolved on rank 0, concatenation (include/sdfmesh.h)
+    def shard_local_weld(self) -> dict:
+        w = _ShardWeld()
+        self._check(self._lib.sdm_shard_local_weld(self._h, ctypes.byref(w)))
+        return {n: getattr(w, n) for n, _ in _ShardWeld._fields_}
+
+    def shard_boundary_keys(self, intervals):
+        """intervals: [(lo, hi)] closed x intervals (the other shards' ranges) -> (device pointer to rows of 4 u32, row count)."""
+        n = len(intervals)
+        lo = (ctypes.c_float * max(n, 1))(*[a for a, _ in intervals])
+        hi = (ctypes.c_float * max(n, 1))(*[b for _, b in intervals])
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_uint32(0)
+        self._check(self._lib.sdm_shard_boundary_keys(self._h, lo, hi, ctypes.c_uint32(n), ctypes.byref(ptr), ctypes.byref(cnt)))
+        return int(ptr.value or 0), int(cnt.value)
+
+    def shard_key_scratch(self, rows: int) -> int:
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.sdm_shard_key_scratch(self._h, ctypes.c_uint32(rows), ctypes.byref(ptr)))
+        return int(ptr.value or 0)
+
+    def shard_resolve(self, rows_ptr: int, total_rows: int, vertex_counts) -> dict:
+        n = len(vertex_counts)
+        vc = (ctypes.c_uint32 * n)(*vertex_counts)
+        removed, goff = (ctypes.c_uint32 * n)(), (ctypes.c_uint32 * n)()
+        pairs, failed = ctypes.c_void_p(), ctypes.c_uint32(0)
+        self._check(self._lib.sdm_shard_resolve(self._h, ctypes.c_void_p(rows_ptr), ctypes.c_uint32(total_rows), vc, ctypes.c_uint32(n), removed, goff,
+                                                ctypes.byref(pairs), ctypes.byref(failed)))
+        return dict(removed=list(removed), global_offset=list(goff), pairs=int(pairs.value or 0), failed=bool(failed.value))
+
+    def shard_pair_scratch(self, pairs: int) -> int:
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.sdm_shard_pair_scratch(self._h, ctypes.c_uint32(pairs), ctypes.byref(ptr)))
+        return int(ptr.value or 0)
+
+    def shard_apply_remap(self, pairs_ptr: int, pair_count: int, global_offset: int) -> None:
+        self._check(self._lib.sdm_shard_apply_remap(self._h, ctypes.c_void_p(pairs_ptr), ctypes.c_uint32(pair_count), ctypes.c_uint32(global_offset)))
+
+    def shard_welded_buffers(self) -> dict:
+        b = _ShardBuffers()
+        self._check(self._lib.sdm_shard_welded_buffers(self._h, ctypes.byref(b)))
+        return dict(positions=int(b.positions or 0), normals=int(b.normals or 0), indices=int(b.triangle_vertex_ids or 0))
+
+    def shard_reserve_welded(self, total_vertices: int, total_triangles: int) -> None:
+        self._check(self._lib.sdm_shard_reserve_welded(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles)))
+
+    def shard_finish(self, total_vertices: int, total_triangles: int, download: bool = False):
+        m = _Mesh()
+        self._check(self._lib.sdm_shard_finish(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles), ctypes.byref(m)))
         return self._download(m) if download else m
 
     def download_into(self, m, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:

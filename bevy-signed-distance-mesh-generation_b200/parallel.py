@@ -1,5 +1,6 @@
-"""Multi-GPU remesh: contiguous shards of the active list, one process / handle per GPU, mesh shards gathered to
-rank 0 over NVLink with NCCL (torch.distributed), welded there into exactly the single-GPU mesh.
+"""Multi-GPU remesh: contiguous shards of the active list, one process / handle per GPU; every shard is welded where it was
+made, the keys shared along the shard interfaces are resolved on rank 0, and the welded shards are gathered to rank 0 over
+NVLink with NCCL (torch.distributed) into exactly the single-GPU mesh.
 
 Why this shape: every voxel's classification, vertices and normals depend only on its own corner
 coordinates and the analytic SDF (compute_mesh_generation.cu:27-58, 74-86) - no halo is needed - and the list is
@@ -74,55 +75,119 @@ class ShardedRemesher:
         return {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
 
     # -- N GPUs ---------------------------------------------------------------------------------------
+    def _exchange(self, torch, dev, send, recv_root):
+        """One grouped NCCL send/recv towards rank 0.  send: [(device pointer, element count, typestr)] of this rank (ranks > 0);
+        recv_root(r): the same for rank r's rows inside rank 0's buffers."""
+        dist = self.dist
+        ops = []
+        if self.rank == 0:
+            for r in range(1, self.world):
+                ops += [dist.P2POp(dist.irecv, _view(torch, p, n, ts, dev), r) for p, n, ts in recv_root(r) if n]
+        else:
+            ops += [dist.P2POp(dist.isend, _view(torch, p, n, ts, dev), 0) for p, n, ts in send if n]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        torch.cuda.current_stream().synchronize()
+
     def _step_sharded(self):
+        """Local shard -> local weld -> the keys shared along the shard interfaces are resolved on rank 0 -> every rank drops its
+        duplicates and makes its indices global -> the welded shards are concatenated on rank 0 (include/sdfmesh.h, "Distributed
+        weld").  If that is not possible (non-finite vertices, scratch too small) the intermediate lists are gathered and rank 0
+        welds everything, as in the first version."""
         import torch
 
         dist, h = self.dist, self.h
         dev = torch.device("cuda", torch.cuda.current_device())
         tm = [time.perf_counter()]
         info = h.shard_remesh(self.bb, self.init, self.levels, self.split_level, self.rank, self.world)
-        tm.append(time.perf_counter())
         gpu_ms = h.stats()["last_gpu_ms"]
-        mine = torch.tensor([info["unique_vertices"], info["raw_triangles"]], dtype=torch.int64, device=dev)
-        allc = torch.empty((self.world, 2), dtype=torch.int64, device=dev)
+        w = h.shard_local_weld()
+        gpu_ms += h.stats()["last_gpu_ms"]
+        tm.append(time.perf_counter())
+        mine = torch.tensor([w["vertices"], w["triangles"], w["nonfinite"], info["unique_vertices"], info["raw_triangles"], w["min_x"], w["max_x"]],
+                            dtype=torch.float64, device=dev)
+        allc = torch.empty((self.world, 7), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allc, mine)
-        counts = [(int(a), int(b)) for a, b in allc.cpu().tolist()]
-        tm.append(time.perf_counter())
-        v_off, t_off, (V, T) = plan_offsets(counts)
-        ops = []
-        if self.rank == 0:
-            h.shard_reserve(V, T)
-            b = h.shard_buffers()
-            for r in range(1, self.world):
-                u, tr = counts[r]
-                if u:
-                    ops.append(dist.P2POp(dist.irecv, _view(torch, b["positions"] + 12 * v_off[r], 3 * u, "<f4", dev), r))
-                    ops.append(dist.P2POp(dist.irecv, _view(torch, b["normals"] + 12 * v_off[r], 3 * u, "<f4", dev), r))
-                if tr:
-                    ops.append(dist.P2POp(dist.irecv, _view(torch, b["triangle_vertex_ids"] + 12 * t_off[r], 3 * tr, "<i4", dev), r))
-        else:
-            h.shard_prepare_send(v_off[self.rank])
-            b = h.shard_buffers()
-            u, tr = counts[self.rank]
-            if u:
-                ops.append(dist.P2POp(dist.isend, _view(torch, b["positions"], 3 * u, "<f4", dev), 0))
-                ops.append(dist.P2POp(dist.isend, _view(torch, b["normals"], 3 * u, "<f4", dev), 0))
-            if tr:
-                ops.append(dist.P2POp(dist.isend, _view(torch, b["triangle_vertex_ids"], 3 * tr, "<i4", dev), 0))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        torch.cuda.current_stream().synchronize()
-        tm.append(time.perf_counter())
+        rows_all = allc.cpu().tolist()
+        counts = [[int(x) for x in row[:5]] for row in rows_all]
+        ranges = [(row[5], row[6]) for row in rows_all]
+        fallback = any(c[2] for c in counts) or self.world > 32
         out = {"triangles": 0, "vertices": 0}
-        if self.rank == 0:
-            m = h.shard_weld(V, T)
-            gpu_ms += h.stats()["last_gpu_ms"]
-            self.mesh = m
-            out = {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
-        self.last_gpu_ms = gpu_ms
+        if not fallback:
+            # candidates: my welded vertices inside another shard's x range (equal keys are < 1.1e-5 apart; widened by 1e-4)
+            ivals = [(lo - 1e-4, hi + 1e-4) for r, (lo, hi) in enumerate(ranges) if r != self.rank and lo <= hi]
+            kptr, kcnt = h.shard_boundary_keys(ivals)
+            allk = torch.empty((self.world,), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allk, torch.tensor([kcnt], dtype=torch.int64, device=dev))
+            kcounts = [int(x) for x in allk.cpu().tolist()]
+            k_off = plan_offsets([(k, 0) for k in kcounts])[0]
+            tm.append(time.perf_counter())
+            # verdict: [failed, then per shard: removed vertices, global vertex offset]
+            verdict = torch.zeros(1 + 2 * self.world, dtype=torch.int64, device=dev)
+            res = None
+            if self.rank == 0:
+                base = h.shard_key_scratch(sum(kcounts))   # rank 0's own rows already sit at the front of this scratch
+                self._exchange(torch, dev, None, lambda r: [(base + 16 * k_off[r], 4 * kcounts[r], "<i4")])
+                res = h.shard_resolve(base, sum(kcounts), [c[0] for c in counts])
+                verdict = torch.tensor([int(res["failed"])] + res["removed"] + res["global_offset"], dtype=torch.int64, device=dev)
+            else:
+                self._exchange(torch, dev, [(kptr, 4 * kcnt, "<i4")], None)
+            dist.broadcast(verdict, 0)
+            vd = [int(x) for x in verdict.cpu().tolist()]
+            fallback = bool(vd[0])
+            removed, goff = vd[1:1 + self.world], vd[1 + self.world:]
+            tm.append(time.perf_counter())
+        if not fallback:
+            p_off = plan_offsets([(n, 0) for n in removed])[0]
+            kept = [c[0] - d for c, d in zip(counts, removed)]
+            t_off = plan_offsets([(0, c[1]) for c in counts])[1]
+            V, T = sum(kept), sum(c[1] for c in counts)
+            if self.rank == 0:
+                # the duplicate pairs go out, the welded rows come in: one grouped exchange each way
+                ops = [dist.P2POp(dist.isend, _view(torch, res["pairs"] + 8 * p_off[r], 2 * removed[r], "<i4", dev), r) for r in range(1, self.world) if removed[r]]
+                if ops:
+                    for q in dist.batch_isend_irecv(ops):
+                        q.wait()
+                h.shard_reserve_welded(V, T)
+                b = h.shard_welded_buffers()
+                self._exchange(torch, dev, None, lambda r: [(b["positions"] + 12 * goff[r], 3 * kept[r], "<f4"), (b["normals"] + 12 * goff[r], 3 * kept[r], "<f4"),
+                                                            (b["indices"] + 12 * t_off[r], 3 * counts[r][1], "<i4")])
+                m = h.shard_finish(V, T)
+                self.mesh = m
+                out = {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
+            else:
+                n = removed[self.rank]
+                pptr = h.shard_pair_scratch(n)
+                if n:
+                    for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, _view(torch, pptr, 2 * n, "<i4", dev), 0)]):
+                        q.wait()
+                    torch.cuda.current_stream().synchronize()
+                h.shard_apply_remap(pptr, n, goff[self.rank])
+                b = h.shard_welded_buffers()
+                self._exchange(torch, dev, [(b["positions"], 3 * kept[self.rank], "<f4"), (b["normals"], 3 * kept[self.rank], "<f4"),
+                                            (b["indices"], 3 * counts[self.rank][1], "<i4")], None)
+        else:
+            v_off, t_off, (V, T) = plan_offsets([(c[3], c[4]) for c in counts])
+            if self.rank == 0:
+                h.shard_reserve(V, T)
+                b = h.shard_buffers()
+                self._exchange(torch, dev, None, lambda r: [(b["positions"] + 12 * v_off[r], 3 * counts[r][3], "<f4"),
+                                                            (b["normals"] + 12 * v_off[r], 3 * counts[r][3], "<f4"),
+                                                            (b["triangle_vertex_ids"] + 12 * t_off[r], 3 * counts[r][4], "<i4")])
+                m = h.shard_weld(V, T)
+                gpu_ms += h.stats()["last_gpu_ms"]
+                self.mesh = m
+                out = {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
+            else:
+                h.shard_prepare_send(v_off[self.rank])
+                b = h.shard_buffers()
+                self._exchange(torch, dev, [(b["positions"], 3 * counts[self.rank][3], "<f4"), (b["normals"], 3 * counts[self.rank][3], "<f4"),
+                                            (b["triangle_vertex_ids"], 3 * counts[self.rank][4], "<i4")], None)
         tm.append(time.perf_counter())
-        # host-side phase times of the last step (ms): local shard, count all-gather, gather, weld
+        self.last_gpu_ms = gpu_ms
+        self.last_fallback = fallback
+        # host-side phase times of the last step (ms): local shard + local weld, counts / ranges / boundary keys, resolve, gather
         self.last_phases = [round((b - a) * 1e3, 3) for a, b in zip(tm[:-1], tm[1:])]
         return out
 

@@ -51,3 +51,62 @@ def test_sharded_mesh_equals_single(scene_name, init, levels, split, G):
     finally:
         for h in hs:
             h.close()
+
+
+@pytest.mark.parametrize("scene_name,init,levels,split,G", [("sd_obj", 32, 3, 1, 2), ("sd_obj", 32, 3, 2, 3), ("many64", 32, 2, 1, 4),
+                                                            ("sphere_box", 32, 2, 1, 2), ("sd_obj", 32, 2, 2, 7), ("sd_obj", 32, 2, 0, 1)])
+def test_distributed_weld_equals_single(scene_name, init, levels, split, G):
+    """The preferred exchange (include/sdfmesh.h, "Distributed weld"): every shard welds locally, rank 0 resolves the keys the
+    shards share along their interfaces, duplicates are dropped and re-mapped, the shards are concatenated.  Same bytes as the
+    single-handle mesh."""
+    import torch
+
+    scene = scenes.many_primitives(64) if scene_name == "many64" else scenes.SCENES[scene_name]()
+    dev = torch.device("cuda", 0)
+    hs = [bsdmg_b200.CudaHandler(0, scene) for _ in range(G)]
+    copy = lambda dst, src, n, ts: n and parallel._view(torch, dst, n, ts, dev).copy_(parallel._view(torch, src, n, ts, dev))
+    try:
+        single = hs[0].remesh(5.0, init, levels)
+        for r, h in enumerate(hs):
+            h.shard_remesh(5.0, init, levels, split, r, G)
+        ws = [h.shard_local_weld() for h in hs]
+        assert all(w["nonfinite"] == 0 for w in ws)
+        rows = []
+        for r, h in enumerate(hs):
+            ivals = [(w["min_x"] - 1e-4, w["max_x"] + 1e-4) for q, w in enumerate(ws) if q != r and w["min_x"] <= w["max_x"]]
+            rows.append(h.shard_boundary_keys(ivals))
+        k_off, _, (K, _) = parallel.plan_offsets([(n, 0) for _, n in rows])
+        base = hs[0].shard_key_scratch(K)
+        for r in range(1, G):
+            copy(base + 16 * k_off[r], rows[r][0], 4 * rows[r][1], "<i4")
+        torch.cuda.synchronize()
+        res = hs[0].shard_resolve(base, K, [w["vertices"] for w in ws])
+        assert not res["failed"] and res["removed"][0] == 0
+        if G > 1 and scene_name == "sd_obj":
+            assert sum(res["removed"]) > 0                       # neighbouring shards mesh the edges of their interface twice
+        p_off = parallel.plan_offsets([(n, 0) for n in res["removed"]])[0]
+        kept = [w["vertices"] - d for w, d in zip(ws, res["removed"])]
+        V, T = sum(kept), sum(w["triangles"] for w in ws)
+        assert (V, T) == (single.vertex_count, single.triangle_count)
+        assert res["global_offset"] == parallel.plan_offsets([(k, 0) for k in kept])[0]
+        t_off = parallel.plan_offsets([(0, w["triangles"]) for w in ws])[1]
+        for r in range(1, G):
+            dst = hs[r].shard_pair_scratch(res["removed"][r])
+            copy(dst, res["pairs"] + 8 * p_off[r], 2 * res["removed"][r], "<i4")
+            torch.cuda.synchronize()
+            hs[r].shard_apply_remap(dst, res["removed"][r], res["global_offset"][r])
+        hs[0].shard_reserve_welded(V, T)
+        root = hs[0].shard_welded_buffers()
+        for r in range(1, G):
+            b = hs[r].shard_welded_buffers()
+            copy(root["positions"] + 12 * res["global_offset"][r], b["positions"], 3 * kept[r], "<f4")
+            copy(root["normals"] + 12 * res["global_offset"][r], b["normals"], 3 * kept[r], "<f4")
+            copy(root["indices"] + 12 * t_off[r], b["indices"], 3 * ws[r]["triangles"], "<i4")
+        torch.cuda.synchronize()
+        merged = hs[0].shard_finish(V, T, download=True)
+        assert np.array_equal(merged.indices, single.indices)
+        assert np.array_equal(bits(merged.positions), bits(single.positions))
+        assert np.array_equal(bits(merged.normals), bits(single.normals))
+    finally:
+        for h in hs:
+            h.close()
