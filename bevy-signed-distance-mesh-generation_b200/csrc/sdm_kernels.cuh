@@ -1347,7 +1347,11 @@ __global__ void __launch_bounds__(256) k_build_masks_fine(const uint4* __restric
         const float cx = g.ox + ((float) ix + 0.5f) * g.cell, cy = g.oy + ((float) iy + 0.5f) * g.cell, cz = g.oz + ((float) iz + 0.5f) * g.cell;
         const uint32_t* __restrict__ prow = parent_masks + (size_t) pc * g.W;
         for (uint32_t w = 0; w < g.W; w++) rows[lane * 33u + w] = 0u;
-        float U = inf;   // min over earlier candidates of d_j(c) + rho
+        // acc = the scene fold at the cell centre over the primitives kept so far (a dropped primitive would not have changed it),
+        // with the approximate distances: within ~1e-5 of the exact value.  The fold of 1-Lipschitz distances is 1-Lipschitz,
+        // so acc + rho bounds the accumulator on the whole cell from above - a tighter U than min_j d_j(c) + rho wherever
+        // primitives blend - and |acc_final| > rho means the SDF keeps its sign on the cell (zero-crossing flag below).
+        float acc = SDM_MAX_POSITIVE_F32;
         for (uint32_t w = 0; w < g.W; w++) {
             uint32_t pm = __ldg(prow + w);   // warp-uniform
             uint32_t mine = 0;
@@ -1359,8 +1363,10 @@ __global__ void __launch_bounds__(256) k_build_masks_fine(const uint4* __restric
                 const DevPrim c = prims[j];
                 const float d = prim_distance_cull(c, cx, cy, cz);
                 const float kk = c.fold == SDM_FOLD_SMOOTH_MIN ? c.k : 0.0f;
-                if (!(d - rho >= U + kk + 1e-4f)) mine |= 1u << b;   // NaN distance: keep
-                U = fminf(U, d + rho);
+                if (!(d - rho >= (acc + rho) + kk + 1e-4f)) {   // NaN distance: keep
+                    mine |= 1u << b;
+                    acc = c.fold == SDM_FOLD_SMOOTH_MIN ? smooth_min_skip(acc, d, c.k) : fminf(acc, d);
+                }
             }
             rows[lane * 33u + w] = mine;
         }
@@ -1371,10 +1377,9 @@ __global__ void __launch_bounds__(256) k_build_masks_fine(const uint4* __restric
             const size_t cell = ((size_t) rx * g.G + ry) * g.G + rz;
             if (lane < g.W) out_masks[cell * g.W + lane] = rows[r * 33u + lane];
         }
-        if (out_maybe) {   // zero-crossing flag, see k_build_masks
-            const float min_d = U - rho;
-            const bool empty = (min_d - rho - hdr.kmax > 1e-4f) || (min_d + rho < -1e-4f);
-            out_maybe[((size_t) ix * g.G + iy) * g.G + iz] = empty ? 0 : 1;
+        if (out_maybe) {   // zero-crossing flag: |sd(p) - sd(c)| <= rho on the cell, acc is sd(c) to ~1e-5
+            const bool empty = fabsf(acc) > rho + 1e-4f;
+            out_maybe[((size_t) ix * g.G + iy) * g.G + iz] = empty ? 0 : 1;   // NaN: not empty
         }
         __syncwarp();
     }
