@@ -241,6 +241,7 @@ struct SdmHandle {
     uint32_t shard_index = 0;
     int welded_set = 0, welded_vset = 0;   // output sets holding the local weld's indices / vertices
     uint32_t welded_v = 0, welded_t = 0;   // rows of the local weld (after sdm_shard_apply_remap: kept vertices)
+    ShardOffsets res_offsets {};      // vertex / duplicate-pair offsets of the last sdm_shard_resolve
     DevBuf<uint32_t> shard_scratch;   // 128 words: x range, counters, per-shard duplicate counts / cursors / offsets
     uint32_t* host_scratch = nullptr; // pinned mirror
     uint32_t own_tris = 0, own_uniq = 0;   // the local shard's counts (sdm_shard_remesh)
@@ -1004,16 +1005,18 @@ int sdm_mesh_download(SdmHandle* h, const SdmMesh* m, float* positions, float* n
 // sdm_remesh may be issued immediately (it writes the other output set).  Host memory should be pinned.
 int sdm_mesh_download_async(SdmHandle* h, const SdmMesh* m, float* positions, float* normals, uint32_t* indices) {
     if (!h || !m) return fail(SDM_ERR_INVALID, "null argument");
-    if (!m->on_device || m->reserved < 0 || m->reserved > 1) return fail(SDM_ERR_INVALID, "not a device mesh of this library");
+    if (!m->on_device || m->reserved < 0 || m->reserved > 7) return fail(SDM_ERR_INVALID, "not a device mesh of this library");
     CK(cudaSetDevice(h->device));
-    const int b = m->reserved;
+    // output set of the indices; a mesh assembled by sdm_shard_fixup keeps its vertices in the other set (reserved = 4 | vset << 1 | iset)
+    const int b = m->reserved & 1, vb = (m->reserved & 4) ? ((m->reserved >> 1) & 1) : b;
     cudaStream_t cs = h->copy_stream;
     CK(cudaStreamWaitEvent(cs, h->ev_mesh_done[b], 0));
     if (m->vertex_count && positions) CK(cudaMemcpyAsync(positions, m->positions, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, cs));
     if (m->vertex_count && normals) CK(cudaMemcpyAsync(normals, m->normals, (size_t) m->vertex_count * 12, cudaMemcpyDeviceToHost, cs));
     if (m->triangle_count && indices) CK(cudaMemcpyAsync(indices, m->indices, (size_t) m->triangle_count * 12, cudaMemcpyDeviceToHost, cs));
     CK(cudaEventRecord(h->ev_copy_done[b], cs));
-    (void) cudaStreamQuery(cs);   // push the copies to the device now: kernels enqueued right behind them must not start first
+    if (vb != b) CK(cudaEventRecord(h->ev_copy_done[vb], cs));   // the next weld into either set waits for this download
+    (void) cudaStreamQuery(cs);   // push the copies to the device now
     return SDM_OK;
 }
 int sdm_mesh_download_wait(SdmHandle* h) {
@@ -1230,6 +1233,7 @@ int sdm_shard_boundary_keys(SdmHandle* h, const float* lo, const float* hi, uint
     for (uint32_t i = 0; i < interval_count; i++) { iv.lo[i] = lo[i]; iv.hi[i] = hi[i]; }
     cudaStream_t s = h->stream;
     const uint32_t cap_rows = h->table_entries;   // the vertex table is free after k_orient: its 16-byte entries hold the rows
+    CK(dev_fill(s, h->shard_scratch.p + 3, 0, 4));   // the candidate counter
     k_shard_boundary_keys<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[h->welded_vset].p, iv, h->shard_index, h->table1.p, cap_rows, h->shard_scratch.p);
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(h->host_scratch, h->shard_scratch.p, 16, cudaMemcpyDeviceToHost, s));
@@ -1247,28 +1251,23 @@ int sdm_shard_key_scratch(SdmHandle* h, uint32_t rows, uint32_t** out_rows_devic
     return SDM_OK;
 }
 
-int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total, const uint32_t* vertex_counts, uint32_t shards,
-                      uint32_t* out_removed, uint32_t* out_goff, uint32_t** out_pairs_device, uint32_t* out_failed) {
-    if (!h || !vertex_counts || !out_removed || !out_goff || !out_pairs_device || !out_failed || (total && !rows_device))
-        return fail(SDM_ERR_INVALID, "null argument");
+int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total, const uint32_t* vertex_counts, uint32_t shards, uint32_t* out_removed) {
+    if (!h || !vertex_counts || !out_removed || (total && !rows_device)) return fail(SDM_ERR_INVALID, "null argument");
     if (shards == 0 || shards > 32) return fail(SDM_ERR_INVALID, "1..32 shards");
     CK(cudaSetDevice(h->device));
     int rc = ensure_shard_scratch(h);
     if (rc) return rc;
-    ShardOffsets so {};
+    ShardOffsets& so = h->res_offsets;
+    so = ShardOffsets {};
     so.count = shards;
     uint64_t vsum = 0;
     for (uint32_t s = 0; s < shards; s++) { so.voff[s] = (uint32_t) vsum; vsum += vertex_counts[s]; }
     so.voff[shards] = (uint32_t) vsum;
-    *out_failed = 0;
-    *out_pairs_device = reinterpret_cast<uint32_t*>(h->slot_ref.p);
     const uint32_t nwords = (uint32_t) (vsum / 32 + 2);
     const uint32_t entries = std::min<uint32_t>(pow2_at_least(std::max<uint64_t>((uint64_t) total * 2, 1024)), h->table_entries);
-    if (vsum >= (1ull << 32) || nwords > h->first_bits.n || nwords > h->first_prefix.n || total > h->wref.n || (uint64_t) total * 2 > h->slot_ref.n ||
-        (uint64_t) entries * 4 < (uint64_t) total * 5) {
-        *out_failed = 1;   // does not fit the root's scratch: the caller falls back to the root weld
-        return SDM_OK;
-    }
+    if (vsum > h->cap_uniq || nwords > h->first_bits.n || nwords > h->first_prefix.n || total > h->wref.n || (uint64_t) total * 2 > h->slot_ref.n ||
+        (uint64_t) entries * 4 < (uint64_t) total * 5)
+        return fail(SDM_ERR_CAPACITY, "call sdm_shard_reserve_welded with the totals first");
     cudaStream_t st = h->stream;
     uint32_t* sc = h->shard_scratch.p;   // [32..64) duplicates per shard, [64..96) cursors, [96..128) global offsets, [4] errors
     CK(dev_fill(st, sc, 0, 128 * 4));
@@ -1282,44 +1281,49 @@ int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total,
     k_scan_bits_1block<<<1, 1024, 0, st>>>(h->first_bits.p, h->first_prefix.p, nwords);
     CK(cudaMemcpyAsync(h->host_scratch, sc, 128 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (h->host_scratch[4]) { *out_failed = 1; return SDM_OK; }
+    if (h->host_scratch[4]) return fail(SDM_ERR_CAPACITY, "key table overflow in sdm_shard_resolve");
     uint32_t psum = 0;
     for (uint32_t s = 0; s < shards; s++) { out_removed[s] = h->host_scratch[32 + s]; so.poff[s] = psum; psum += out_removed[s]; }
     so.poff[shards] = psum;
     k_res_pairs<<<h->g_light, 256, 0, st>>>(reinterpret_cast<const uint4*>(rows_device), total, h->table2.p, h->wref.p, so, h->first_bits.p, h->first_prefix.p,
                                             sc + 64, reinterpret_cast<uint2*>(h->slot_ref.p), sc + 96);
     h->stats.kernel_launches += 7;
-    CK(cudaMemcpyAsync(h->host_scratch, sc, 128 * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (uint32_t s = 0; s < shards; s++) out_goff[s] = h->host_scratch[96 + s];
-    return SDM_OK;
-}
-
-int sdm_shard_pair_scratch(SdmHandle* h, uint32_t pairs, uint32_t** out_pairs_device) {
-    if (!h || !out_pairs_device) return fail(SDM_ERR_INVALID, "null argument");
-    if ((uint64_t) pairs * 2 > h->slot_ref.n) return fail(SDM_ERR_CAPACITY, "too many duplicate pairs");
-    *out_pairs_device = reinterpret_cast<uint32_t*>(h->slot_ref.p);
-    return SDM_OK;
-}
-
-int sdm_shard_apply_remap(SdmHandle* h, const uint32_t* pairs_device, uint32_t npairs, uint32_t global_offset) {
-    if (!h || (npairs && !pairs_device)) return fail(SDM_ERR_INVALID, "null argument");
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    const uint32_t V = h->welded_v;
-    const uint32_t nwords = V / 32 + 2;
-    if (nwords > h->first_bits.n || nwords > h->first_prefix.n || V > h->vidx.n) return fail(SDM_ERR_CAPACITY, "remap scratch too small");
-    const int b = h->welded_set, vb = b ^ 1;
-    CK(dev_fill(st, h->first_bits.p, 0, (size_t) nwords * 4));
-    if (npairs) k_remap_mark<<<h->g_light, 256, 0, st>>>(reinterpret_cast<const uint2*>(pairs_device), npairs, h->first_bits.p, h->vidx.p);
-    k_scan_bits_1block<<<1, 1024, 0, st>>>(h->first_bits.p, h->first_prefix.p, nwords);
-    k_remap_apply<<<h->g_light, 256, 0, st>>>(h->state.p, h->first_bits.p, h->first_prefix.p, h->vidx.p, global_offset, h->out_pos[b].p, h->out_nrm[b].p,
-                                              h->out_pos[vb].p, h->out_nrm[vb].p, h->out_idx[b].p);
-    h->stats.kernel_launches += 4;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));   // the buffers are handed to NCCL on another stream next
+    return SDM_OK;
+}
+
+int sdm_shard_fixup(SdmHandle* h, const uint32_t* triangle_counts, SdmMesh* out_mesh) {
+    if (!h || !triangle_counts || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const ShardOffsets& so = h->res_offsets;
+    if (so.count == 0) return fail(SDM_ERR_INVALID, "sdm_shard_resolve first");
+    ShardTriOffsets to {};
+    to.count = so.count;
+    uint64_t tsum = 0;
+    for (uint32_t s = 0; s < so.count; s++) { to.toff[s] = (uint32_t) tsum; tsum += triangle_counts[s]; }
+    to.toff[so.count] = (uint32_t) tsum;
+    const uint32_t total_v = so.voff[so.count], removed = so.poff[so.count];
+    if (total_v > h->cap_uniq || tsum > h->cap_tris) return fail(SDM_ERR_CAPACITY, "call sdm_shard_reserve_welded with the totals first");
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(h->ev0, st));
+    const int b = h->welded_set, vb = b ^ 1;
+    CK(cudaStreamWaitEvent(st, h->ev_copy_done[vb], 0));   // a download may still be reading the set the vertices move into
+    if (removed) k_fix_scatter<<<h->g_light, 256, 0, st>>>(reinterpret_cast<const uint2*>(h->slot_ref.p), so, h->vidx.p);
+    k_fix_vertices<<<h->g_light, 256, 0, st>>>(total_v, h->first_bits.p, h->first_prefix.p, h->out_pos[b].p, h->out_nrm[b].p, h->out_pos[vb].p, h->out_nrm[vb].p);
+    k_fix_indices<<<h->g_light, 256, 0, st>>>(so, to, h->first_bits.p, h->first_prefix.p, h->vidx.p, h->out_idx[b].p);
+    h->stats.kernel_launches += 3;
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaEventRecord(h->ev_mesh_done[b], st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_gpu_ms = ms;
     h->welded_vset = vb;
-    h->welded_v = V - npairs;
+    out_mesh->positions = h->out_pos[vb].p; out_mesh->normals = h->out_nrm[vb].p; out_mesh->indices = h->out_idx[b].p;
+    out_mesh->vertex_count = total_v - removed; out_mesh->triangle_count = (uint32_t) tsum;
+    out_mesh->on_device = 1; out_mesh->reserved = 4 | (vb << 1) | b;
+    h->res_offsets.count = 0;
     return SDM_OK;
 }
 
@@ -1355,19 +1359,6 @@ int sdm_shard_reserve_welded(SdmHandle* h, uint32_t total_vertices, uint32_t tot
     }
     cudaFree(old_pos); cudaFree(old_nrm); cudaFree(old_idx);
     return rc;
-}
-
-int sdm_shard_finish(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh) {
-    if (!h || !out_mesh) return fail(SDM_ERR_INVALID, "null argument");
-    if (total_vertices > h->cap_uniq || total_triangles > h->cap_tris) return fail(SDM_ERR_CAPACITY, "call sdm_shard_reserve_welded first");
-    CK(cudaSetDevice(h->device));
-    const int b = h->welded_set;
-    CK(cudaEventRecord(h->ev_mesh_done[b], h->stream));   // the received rows were written on other streams: callers synchronise first
-    out_mesh->positions = h->out_pos[h->welded_vset].p; out_mesh->normals = h->out_nrm[h->welded_vset].p; out_mesh->indices = h->out_idx[b].p;
-    out_mesh->vertex_count = total_vertices; out_mesh->triangle_count = total_triangles;
-    out_mesh->on_device = 1; out_mesh->reserved = b;
-    h->stats.last_gpu_ms = 0.0f;
-    return SDM_OK;
 }
 
 int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh) {

@@ -1117,29 +1117,38 @@ __global__ void __launch_bounds__(256) k_res_pairs(const uint4* __restrict__ row
         pairs[slot] = make_uint2(me & 0xFFFFFFu, oc - bit_rank(bitmap, prefix, oc));   // the owner itself is never removed
     }
 }
-// every rank: removal bitmap and owner ids of its own duplicates
-__global__ void __launch_bounds__(256) k_remap_mark(const uint2* __restrict__ pairs, uint32_t npairs, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ remap) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
-        const uint2 p = pairs[i];
-        atomicOr(bitmap + (p.x >> 5), 1u << (p.x & 31u));
-        remap[p.x] = p.y;
+// rank 0, after the welded shards (local indices, duplicates included) have arrived at their concatenated offsets:
+// owner ids of the duplicates into a dense map over the concatenated vertex space ...
+__global__ void __launch_bounds__(256) k_fix_scatter(const uint2* __restrict__ pairs, ShardOffsets so, uint32_t* __restrict__ remap) {
+    const uint32_t total = so.poff[so.count];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t s = 0;
+        while (s + 1 < so.count && i >= so.poff[s + 1]) s++;
+        remap[so.voff[s] + pairs[i].x] = pairs[i].y;
     }
 }
-// kept vertices move up (stable), indices become global
-__global__ void __launch_bounds__(256) k_remap_apply(DevState* st, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ remap,
-                                                     uint32_t goff, const float* __restrict__ in_pos, const float* __restrict__ in_nrm, float* __restrict__ out_pos,
-                                                     float* __restrict__ out_nrm, uint32_t* __restrict__ idx) {
-    const uint32_t V = st->n_verts_out, n3 = 3u * st->n_tris_out;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t i = tid; i < V; i += stride) {
-        if ((bitmap[i >> 5] >> (i & 31u)) & 1u) continue;
-        const uint32_t o = i - bit_rank(bitmap, prefix, i);
+// ... kept vertices move up into the other output set (stable) ...
+__global__ void __launch_bounds__(256) k_fix_vertices(uint32_t total_v, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                                                      const float* __restrict__ in_pos, const float* __restrict__ in_nrm, float* __restrict__ out_pos,
+                                                      float* __restrict__ out_nrm) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total_v; c += gridDim.x * blockDim.x) {
+        if ((bitmap[c >> 5] >> (c & 31u)) & 1u) continue;
+        const uint32_t o = c - bit_rank(bitmap, prefix, c);
 #pragma unroll
-        for (int c = 0; c < 3; c++) { out_pos[3 * (size_t) o + c] = in_pos[3 * (size_t) i + c]; out_nrm[3 * (size_t) o + c] = in_nrm[3 * (size_t) i + c]; }
+        for (int k = 0; k < 3; k++) { out_pos[3 * (size_t) o + k] = in_pos[3 * (size_t) c + k]; out_nrm[3 * (size_t) o + k] = in_nrm[3 * (size_t) c + k]; }
     }
-    for (uint32_t j = tid; j < n3; j += stride) {
-        const uint32_t i = idx[j];
-        idx[j] = ((bitmap[i >> 5] >> (i & 31u)) & 1u) ? remap[i] : goff + i - bit_rank(bitmap, prefix, i);
+}
+// ... and every index becomes global: shard-local index -> concatenated position -> owner id or own rank
+struct ShardTriOffsets { uint32_t toff[33]; uint32_t count; };
+__global__ void __launch_bounds__(256) k_fix_indices(ShardOffsets so, ShardTriOffsets to, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                                                     const uint32_t* __restrict__ remap, uint32_t* __restrict__ idx) {
+    const uint32_t n3 = 3u * to.toff[to.count];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n3; j += gridDim.x * blockDim.x) {
+        const uint32_t t = j / 3u;
+        uint32_t s = 0;
+        while (s + 1 < to.count && t >= to.toff[s + 1]) s++;
+        const uint32_t c = so.voff[s] + idx[j];
+        idx[j] = ((bitmap[c >> 5] >> (c & 31u)) & 1u) ? remap[c] : c - bit_rank(bitmap, prefix, c);
     }
 }
 

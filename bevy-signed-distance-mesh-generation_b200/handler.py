@@ -86,8 +86,8 @@ ABI_SYMBOLS = [
     "sdm_voxel_field_to_mesh", "sdm_mesh_free", "sdm_field_reset", "sdm_field_upload", "sdm_field_refine", "sdm_field_count",
     "sdm_field_download", "sdm_field_cases", "sdm_field_to_mesh", "sdm_remesh", "sdm_mesh_download", "sdm_field_triangle_soup",
     "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
-    "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_pair_scratch",
-    "sdm_shard_apply_remap", "sdm_shard_welded_buffers", "sdm_shard_reserve_welded", "sdm_shard_finish",
+    "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_fixup",
+    "sdm_shard_welded_buffers", "sdm_shard_reserve_welded",
     "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
 
@@ -377,22 +377,20 @@ class CudaHandler:
         self._check(self._lib.sdm_shard_key_scratch(self._h, ctypes.c_uint32(rows), ctypes.byref(ptr)))
         return int(ptr.value or 0)
 
-    def shard_resolve(self, rows_ptr: int, total_rows: int, vertex_counts) -> dict:
+    def shard_resolve(self, rows_ptr: int, total_rows: int, vertex_counts) -> list:
+        """rank 0: resolves the gathered key rows; returns the number of removed (duplicate) vertices per shard."""
         n = len(vertex_counts)
         vc = (ctypes.c_uint32 * n)(*vertex_counts)
-        removed, goff = (ctypes.c_uint32 * n)(), (ctypes.c_uint32 * n)()
-        pairs, failed = ctypes.c_void_p(), ctypes.c_uint32(0)
-        self._check(self._lib.sdm_shard_resolve(self._h, ctypes.c_void_p(rows_ptr), ctypes.c_uint32(total_rows), vc, ctypes.c_uint32(n), removed, goff,
-                                                ctypes.byref(pairs), ctypes.byref(failed)))
-        return dict(removed=list(removed), global_offset=list(goff), pairs=int(pairs.value or 0), failed=bool(failed.value))
+        removed = (ctypes.c_uint32 * n)()
+        self._check(self._lib.sdm_shard_resolve(self._h, ctypes.c_void_p(rows_ptr), ctypes.c_uint32(total_rows), vc, ctypes.c_uint32(n), removed))
+        return list(removed)
 
-    def shard_pair_scratch(self, pairs: int) -> int:
-        ptr = ctypes.c_void_p()
-        self._check(self._lib.sdm_shard_pair_scratch(self._h, ctypes.c_uint32(pairs), ctypes.byref(ptr)))
-        return int(ptr.value or 0)
-
-    def shard_apply_remap(self, pairs_ptr: int, pair_count: int, global_offset: int) -> None:
-        self._check(self._lib.sdm_shard_apply_remap(self._h, ctypes.c_void_p(pairs_ptr), ctypes.c_uint32(pair_count), ctypes.c_uint32(global_offset)))
+    def shard_fixup(self, triangle_counts, download: bool = False):
+        """rank 0: after the welded shards have arrived at their concatenated offsets - drops duplicates, makes indices global."""
+        tc = (ctypes.c_uint32 * len(triangle_counts))(*triangle_counts)
+        m = _Mesh()
+        self._check(self._lib.sdm_shard_fixup(self._h, tc, ctypes.byref(m)))
+        return self._download(m) if download else m
 
     def shard_welded_buffers(self) -> dict:
         b = _ShardBuffers()
@@ -401,11 +399,6 @@ class CudaHandler:
 
     def shard_reserve_welded(self, total_vertices: int, total_triangles: int) -> None:
         self._check(self._lib.sdm_shard_reserve_welded(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles)))
-
-    def shard_finish(self, total_vertices: int, total_triangles: int, download: bool = False):
-        m = _Mesh()
-        self._check(self._lib.sdm_shard_finish(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles), ctypes.byref(m)))
-        return self._download(m) if download else m
 
     def download_into(self, m, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:
         """sdm_mesh_download into caller-provided (e.g. pinned) host memory."""

@@ -115,6 +115,9 @@ class ShardedRemesher:
         fallback = any(c[2] for c in counts) or self.world > 32
         out = {"triangles": 0, "vertices": 0}
         if not fallback:
+            v_off, t_off, (VS, T) = plan_offsets([(c[0], c[1]) for c in counts])
+            if self.rank == 0:
+                h.shard_reserve_welded(VS, T)          # before the key rows are extracted: a re-allocation would lose them
             # candidates: my welded vertices inside another shard's x range (equal keys are < 1.1e-5 apart; widened by 1e-4)
             ivals = [(lo - 1e-4, hi + 1e-4) for r, (lo, hi) in enumerate(ranges) if r != self.rank and lo <= hi]
             kptr, kcnt = h.shard_boundary_keys(ivals)
@@ -123,50 +126,31 @@ class ShardedRemesher:
             kcounts = [int(x) for x in allk.cpu().tolist()]
             k_off = plan_offsets([(k, 0) for k in kcounts])[0]
             tm.append(time.perf_counter())
-            # verdict: [failed, then per shard: removed vertices, global vertex offset]
-            verdict = torch.zeros(1 + 2 * self.world, dtype=torch.int64, device=dev)
-            res = None
+            b = h.shard_welded_buffers()
             if self.rank == 0:
                 base = h.shard_key_scratch(sum(kcounts))   # rank 0's own rows already sit at the front of this scratch
                 self._exchange(torch, dev, None, lambda r: [(base + 16 * k_off[r], 4 * kcounts[r], "<i4")])
-                res = h.shard_resolve(base, sum(kcounts), [c[0] for c in counts])
-                verdict = torch.tensor([int(res["failed"])] + res["removed"] + res["global_offset"], dtype=torch.int64, device=dev)
-            else:
-                self._exchange(torch, dev, [(kptr, 4 * kcnt, "<i4")], None)
-            dist.broadcast(verdict, 0)
-            vd = [int(x) for x in verdict.cpu().tolist()]
-            fallback = bool(vd[0])
-            removed, goff = vd[1:1 + self.world], vd[1 + self.world:]
-            tm.append(time.perf_counter())
-        if not fallback:
-            p_off = plan_offsets([(n, 0) for n in removed])[0]
-            kept = [c[0] - d for c, d in zip(counts, removed)]
-            t_off = plan_offsets([(0, c[1]) for c in counts])[1]
-            V, T = sum(kept), sum(c[1] for c in counts)
-            if self.rank == 0:
-                # the duplicate pairs go out, the welded rows come in: one grouped exchange each way
-                ops = [dist.P2POp(dist.isend, _view(torch, res["pairs"] + 8 * p_off[r], 2 * removed[r], "<i4", dev), r) for r in range(1, self.world) if removed[r]]
-                if ops:
-                    for q in dist.batch_isend_irecv(ops):
-                        q.wait()
-                h.shard_reserve_welded(V, T)
-                b = h.shard_welded_buffers()
-                self._exchange(torch, dev, None, lambda r: [(b["positions"] + 12 * goff[r], 3 * kept[r], "<f4"), (b["normals"] + 12 * goff[r], 3 * kept[r], "<f4"),
-                                                            (b["indices"] + 12 * t_off[r], 3 * counts[r][1], "<i4")])
-                m = h.shard_finish(V, T)
+                # the welded shards (local indices, duplicates included) arrive at their concatenated offsets while the keys are resolved
+                ops = []
+                for r in range(1, self.world):
+                    ops += [dist.P2POp(dist.irecv, _view(torch, p, n, ts, dev), r) for p, n, ts in
+                            ((b["positions"] + 12 * v_off[r], 3 * counts[r][0], "<f4"), (b["normals"] + 12 * v_off[r], 3 * counts[r][0], "<f4"),
+                             (b["indices"] + 12 * t_off[r], 3 * counts[r][1], "<i4")) if n]
+                works = dist.batch_isend_irecv(ops) if ops else []
+                removed = h.shard_resolve(base, sum(kcounts), [c[0] for c in counts])
+                tm.append(time.perf_counter())
+                for q in works:
+                    q.wait()
+                torch.cuda.current_stream().synchronize()
+                m = h.shard_fixup([c[1] for c in counts])
+                gpu_ms += h.stats()["last_gpu_ms"]
                 self.mesh = m
                 out = {"triangles": int(m.triangle_count), "vertices": int(m.vertex_count)}
             else:
-                n = removed[self.rank]
-                pptr = h.shard_pair_scratch(n)
-                if n:
-                    for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, _view(torch, pptr, 2 * n, "<i4", dev), 0)]):
-                        q.wait()
-                    torch.cuda.current_stream().synchronize()
-                h.shard_apply_remap(pptr, n, goff[self.rank])
-                b = h.shard_welded_buffers()
-                self._exchange(torch, dev, [(b["positions"], 3 * kept[self.rank], "<f4"), (b["normals"], 3 * kept[self.rank], "<f4"),
-                                            (b["indices"], 3 * counts[self.rank][1], "<i4")], None)
+                self._exchange(torch, dev, [(kptr, 4 * kcnt, "<i4")], None)
+                tm.append(time.perf_counter())
+                self._exchange(torch, dev, [(b["positions"], 3 * w["vertices"], "<f4"), (b["normals"], 3 * w["vertices"], "<f4"),
+                                            (b["indices"], 3 * w["triangles"], "<i4")], None)
         else:
             v_off, t_off, (V, T) = plan_offsets([(c[3], c[4]) for c in counts])
             if self.rank == 0:
@@ -187,7 +171,8 @@ class ShardedRemesher:
         tm.append(time.perf_counter())
         self.last_gpu_ms = gpu_ms
         self.last_fallback = fallback
-        # host-side phase times of the last step (ms): local shard + local weld, counts / ranges / boundary keys, resolve, gather
+        # host-side phase times of the last step (ms): local shard + local weld, counts / ranges / boundary keys, key gather + resolve,
+        # rest of the shard gather + fix-up (root-weld fallback: gather + weld)
         self.last_phases = [round((b - a) * 1e3, 3) for a, b in zip(tm[:-1], tm[1:])]
         return out
 

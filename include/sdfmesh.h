@@ -199,20 +199,20 @@ int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangl
 /* Distributed weld - the exchange of SURVEY.md section 8e; preferred, the calls above remain as its fallback.
  * Shards share vertices along their interfaces (and wherever two vertices have the same quantised key, src/cuda/mod.rs:270).
  * Global first-occurrence order is shard-major, so a key belongs to its copy in the LOWEST shard; the other copies are
- * removed and their indices re-mapped:
+ * removed and the indices that used them re-mapped:
  *   every rank : sdm_shard_local_weld      - welds its own shard (local order, local indices), reports the x range of its vertices
+ *   rank 0     : sdm_shard_reserve_welded  - room for all shards' welded rows (call before sdm_shard_boundary_keys)
  *   every rank : sdm_shard_boundary_keys   - rows (kx, ky, kz, shard << 24 | local index) of its welded vertices whose x lies
  *                                            inside another shard's x range: only those can share a key with another shard
- *   transport  : the rows are gathered into rank 0's sdm_shard_key_scratch
- *   rank 0     : sdm_shard_resolve         - per shard: number of removed vertices, global vertex offset, and the list of
- *                                            (local index, global id of the owner) pairs of its removed vertices
- *   transport  : every rank > 0 receives its pairs into its sdm_shard_pair_scratch
- *   ranks > 0  : sdm_shard_apply_remap     - drops the removed vertices (stable), makes the indices global
- *   transport  : welded buffers (sdm_shard_welded_buffers) to rank 0 at the global offsets
- *   rank 0     : sdm_shard_reserve_welded(totals) before receiving, sdm_shard_finish(totals) after.
- * If a shard reports non-finite vertices, 2^24 or more vertices, or rank 0 reports `failed`, the ranks fall back to
- * sdm_shard_prepare_send / sdm_shard_reserve / sdm_shard_weld.  Either way the merged mesh is byte-identical to the
- * single-GPU mesh. */
+ *   transport  : the rows are gathered into rank 0's sdm_shard_key_scratch; the welded buffers (sdm_shard_welded_buffers) of
+ *                shard s go to rank 0's welded buffers at the concatenated offsets (vertices / triangles of the shards
+ *                before s) - still with local indices and duplicates, so this transfer needs no answer from rank 0 and
+ *                overlaps the next call
+ *   rank 0     : sdm_shard_resolve         - key table over the rows (smallest (shard, index) per key = the owner), removal
+ *                                            bitmap over the concatenated vertex lists and its prefix pop-count
+ *   rank 0     : sdm_shard_fixup           - drops the removed vertices (stable), makes every index global, hands out the mesh.
+ * If a shard reports non-finite vertices or 2^24 or more vertices, the ranks fall back to sdm_shard_prepare_send /
+ * sdm_shard_reserve / sdm_shard_weld.  Either way the merged mesh is byte-identical to the single-GPU mesh. */
 typedef struct SdmShardWeld {
     uint32_t vertices;               /* welded vertices of this shard */
     uint32_t triangles;              /* kept triangles of this shard */
@@ -220,18 +220,15 @@ typedef struct SdmShardWeld {
     float min_x, max_x;              /* range of x over the finite welded vertices (min_x > max_x: none) */
 } SdmShardWeld;
 int sdm_shard_local_weld(SdmHandle* h, SdmShardWeld* out);
+int sdm_shard_reserve_welded(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles);
 int sdm_shard_boundary_keys(SdmHandle* h, const float* lo, const float* hi, uint32_t interval_count /* <= 32 */,
                             uint32_t** out_rows_device /* [count][4] */, uint32_t* out_count);
 int sdm_shard_key_scratch(SdmHandle* h, uint32_t rows, uint32_t** out_rows_device);
-int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total_rows, const uint32_t* vertex_counts, uint32_t shard_count /* <= 32 */,
-                      uint32_t* out_removed /* [shard_count] */, uint32_t* out_global_offset /* [shard_count] */,
-                      uint32_t** out_pairs_device /* [sum removed][2], grouped by shard */, uint32_t* out_failed);
-int sdm_shard_pair_scratch(SdmHandle* h, uint32_t pairs, uint32_t** out_pairs_device);
-int sdm_shard_apply_remap(SdmHandle* h, const uint32_t* pairs_device, uint32_t pair_count, uint32_t global_offset);
 /* positions / normals: welded rows; triangle_vertex_ids: the welded index buffer */
 int sdm_shard_welded_buffers(SdmHandle* h, SdmShardBuffers* out);
-int sdm_shard_reserve_welded(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles);
-int sdm_shard_finish(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangles, SdmMesh* out_mesh);
+int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total_rows, const uint32_t* vertex_counts, uint32_t shard_count /* <= 32 */,
+                      uint32_t* out_removed /* [shard_count] */);
+int sdm_shard_fixup(SdmHandle* h, const uint32_t* triangle_counts /* [shard_count of the last sdm_shard_resolve] */, SdmMesh* out_mesh);
 
 /* ---- counters for the bench ------------------------------------------------------------------------ */
 typedef struct SdmStats {

@@ -75,35 +75,28 @@ def test_distributed_weld_equals_single(scene_name, init, levels, split, G):
         for r, h in enumerate(hs):
             ivals = [(w["min_x"] - 1e-4, w["max_x"] + 1e-4) for q, w in enumerate(ws) if q != r and w["min_x"] <= w["max_x"]]
             rows.append(h.shard_boundary_keys(ivals))
+        v_off, t_off, (VS, T) = parallel.plan_offsets([(w["vertices"], w["triangles"]) for w in ws])
+        # (rank 0 reserves before it extracts its own key rows: a re-allocation would lose them - so it extracts them again here)
+        hs[0].shard_reserve_welded(VS, T)
+        n0 = rows[0][1]
+        rows[0] = hs[0].shard_boundary_keys([(w["min_x"] - 1e-4, w["max_x"] + 1e-4) for q, w in enumerate(ws) if q != 0 and w["min_x"] <= w["max_x"]])
+        assert rows[0][1] == n0
         k_off, _, (K, _) = parallel.plan_offsets([(n, 0) for _, n in rows])
         base = hs[0].shard_key_scratch(K)
-        for r in range(1, G):
-            copy(base + 16 * k_off[r], rows[r][0], 4 * rows[r][1], "<i4")
-        torch.cuda.synchronize()
-        res = hs[0].shard_resolve(base, K, [w["vertices"] for w in ws])
-        assert not res["failed"] and res["removed"][0] == 0
-        if G > 1 and scene_name == "sd_obj":
-            assert sum(res["removed"]) > 0                       # neighbouring shards mesh the edges of their interface twice
-        p_off = parallel.plan_offsets([(n, 0) for n in res["removed"]])[0]
-        kept = [w["vertices"] - d for w, d in zip(ws, res["removed"])]
-        V, T = sum(kept), sum(w["triangles"] for w in ws)
-        assert (V, T) == (single.vertex_count, single.triangle_count)
-        assert res["global_offset"] == parallel.plan_offsets([(k, 0) for k in kept])[0]
-        t_off = parallel.plan_offsets([(0, w["triangles"]) for w in ws])[1]
-        for r in range(1, G):
-            dst = hs[r].shard_pair_scratch(res["removed"][r])
-            copy(dst, res["pairs"] + 8 * p_off[r], 2 * res["removed"][r], "<i4")
-            torch.cuda.synchronize()
-            hs[r].shard_apply_remap(dst, res["removed"][r], res["global_offset"][r])
-        hs[0].shard_reserve_welded(V, T)
         root = hs[0].shard_welded_buffers()
         for r in range(1, G):
+            copy(base + 16 * k_off[r], rows[r][0], 4 * rows[r][1], "<i4")
             b = hs[r].shard_welded_buffers()
-            copy(root["positions"] + 12 * res["global_offset"][r], b["positions"], 3 * kept[r], "<f4")
-            copy(root["normals"] + 12 * res["global_offset"][r], b["normals"], 3 * kept[r], "<f4")
+            copy(root["positions"] + 12 * v_off[r], b["positions"], 3 * ws[r]["vertices"], "<f4")
+            copy(root["normals"] + 12 * v_off[r], b["normals"], 3 * ws[r]["vertices"], "<f4")
             copy(root["indices"] + 12 * t_off[r], b["indices"], 3 * ws[r]["triangles"], "<i4")
         torch.cuda.synchronize()
-        merged = hs[0].shard_finish(V, T, download=True)
+        removed = hs[0].shard_resolve(base, K, [w["vertices"] for w in ws])
+        assert removed[0] == 0
+        if G > 1 and scene_name == "sd_obj":
+            assert sum(removed) > 0                              # neighbouring shards mesh the edges of their interface twice
+        merged = hs[0].shard_fixup([w["triangles"] for w in ws], download=True)
+        assert (merged.vertex_count, merged.triangle_count) == (VS - sum(removed), T) == (single.vertex_count, single.triangle_count)
         assert np.array_equal(merged.indices, single.indices)
         assert np.array_equal(bits(merged.positions), bits(single.positions))
         assert np.array_equal(bits(merged.normals), bits(single.normals))
