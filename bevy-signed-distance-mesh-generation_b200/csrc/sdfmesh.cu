@@ -504,7 +504,7 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
     k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid,
-                                                 512u);   // vertex chunk per warp (B200 sweep: 256..768 within 3 %)
+                                                 256u);   // vertex chunk per warp (B200 sweep with per-lane culling: 64: 3.82, 128: 3.44, 256: 3.38, 512: 3.59, 1024: 4.08 ms)
     mark(h, "k_project");
     k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid);
     mark(h, "k_project_tail");

@@ -26,7 +26,7 @@ namespace sdm {
 
 namespace cg = cooperative_groups;
 
-enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_REFINE_EMIT = 22, TK_COUNT = 24 };
+enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_REFINE_EMIT = 22, TK_NORMALS = 23, TK_ORIENT = 24, TK_COUNT = 26 };
 enum ErrFlag : uint32_t {
     ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u
 };
@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_TAIL], work);
 }
 
+__device__ __forceinline__ uint32_t tile_group(uint32_t ntiles, uint32_t warps) { return max(1u, min(8u, ntiles / (warps * 4u))); }
 // Inserts vertex u's quantised weld key (src/cuda/mod.rs:270) into the key table with value 0xFFFFFFFF ("no slot yet");
 // returns the entry, counts vertices that met an existing key.
 __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* __restrict__ upos, uint32_t u, uint4* table, uint32_t table_mask) {
@@ -738,7 +739,17 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t table_mask = weld_table_size(n, weld_max_entries) - 1u;   // same size k_clear_weld_state cleared
     unsigned long long work = 0;
-    for (uint32_t u0 = warp_id << 5; u0 < n; u0 += warps_total << 5) {   // warp-uniform trip count (tile masks are warp collectives)
+    // tiles are handed out dynamically, a few at a time (every warp should still get >= ~4 hand-outs): their cost varies with the list
+    // lengths, and a static split left a tail
+    const uint32_t group = tile_group((n + 31u) >> 5, warps_total);
+    for (uint32_t g0 = 0, gk = group;; gk++) {
+        if (gk == group) {
+            if (lane == 0) g0 = atomicAdd(&st->ticket[TK_NORMALS], 32u * group);
+            g0 = __shfl_sync(0xffffffffu, g0, 0);
+            gk = 0;
+        }
+        const uint32_t u0 = g0 + 32u * gk;
+        if (u0 >= n) { if (gk == 0) break; gk = group - 1; continue; }
         const uint32_t u = u0 + lane;
         const bool active = u < n;
         float x = 0.f, y = 0.f, z = 0.f;
@@ -769,7 +780,15 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long work = 0;
-    for (uint32_t t0 = warp_id << 5; t0 < T; t0 += warps_total << 5) {
+    const uint32_t group = tile_group((T + 31u) >> 5, warps_total);
+    for (uint32_t g0 = 0, gk = group;; gk++) {   // dynamic hand-out, see k_vertex_normals
+        if (gk == group) {
+            if (lane == 0) g0 = atomicAdd(&st->ticket[TK_ORIENT], 32u * group);
+            g0 = __shfl_sync(0xffffffffu, g0, 0);
+            gk = 0;
+        }
+        const uint32_t t0 = g0 + 32u * gk;
+        if (t0 >= T) { if (gk == 0) break; gk = group - 1; continue; }
         const uint32_t t = t0 + lane;
         bool valid = false;
         uint32_t u[3] = { 0, 0, 0 };
