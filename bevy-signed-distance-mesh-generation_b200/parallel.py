@@ -34,6 +34,56 @@ def plan_offsets(counts):
     return v_off, t_off, (v, t)
 
 
+def boundary_intervals(ranges, rank: int, widen: float = 1e-4):
+    """x intervals in which a welded vertex of shard `rank` can share its quantised key (src/cuda/mod.rs:270: round(x * 1e5)) with
+    a vertex of another shard: the other shards' [min_x, max_x], widened.  Two equal keys are less than 1.1e-5 apart, so a
+    vertex outside all of these intervals is unique to its shard.  Shards without finite vertices (min > max) contribute nothing."""
+    return [(lo - widen, hi + widen) for r, (lo, hi) in enumerate(ranges) if r != rank and lo <= hi]
+
+
+def weld_keys(positions: np.ndarray) -> np.ndarray:
+    """The reference's weld key (src/cuda/mod.rs:270): (x * 10e4f32).round() as i64 per component, as int64 rows.
+    (Rust's round is half-away-from-zero; `as i64` saturates and sends NaN to 0.)"""
+    c = positions.astype(np.float32) * np.float32(10e4)
+    r = np.where(np.isnan(c), np.float32(0), np.copysign(np.floor(np.abs(c) + np.float32(0.5)), c))
+    r = r.astype(np.float64)
+    big = 9223372036854775808.0                   # 2^63: `as i64` saturates
+    out = np.where(np.abs(r) < big, r, 0.0).astype(np.int64)
+    out[r >= big] = np.iinfo(np.int64).max
+    out[r <= -big] = np.iinfo(np.int64).min
+    return out
+
+
+def concat_welded_shards(shards, candidate_masks=None):
+    """Host restatement of the distributed weld (include/sdfmesh.h; sdm_shard_resolve + sdm_shard_fixup do this on rank 0's
+    GPU).  shards: [(positions[V,3], normals[V,3], indices[T,3])] - each shard welded on its own, local indices, in shard
+    order.  A key's owner is its copy in the LOWEST shard; other copies are removed (stable) and the indices that used them
+    point to the owner.  candidate_masks (optional, per shard, bool[V]): only these vertices are looked at - what
+    boundary_intervals() selects; must give the same result as looking at all of them."""
+    voff = np.cumsum([0] + [p.shape[0] for p, _, _ in shards])
+    owner = {}                                   # key -> concatenated position of its first copy (shards in order = lowest shard)
+    removed = np.zeros(voff[-1], dtype=bool)
+    remap = np.zeros(voff[-1], dtype=np.int64)
+    for s, (pos, _, _) in enumerate(shards):
+        keys = weld_keys(pos)
+        sel = np.arange(pos.shape[0]) if candidate_masks is None else np.nonzero(candidate_masks[s])[0]
+        for i in sel:
+            k = tuple(int(v) for v in keys[i])
+            c = int(voff[s] + i)
+            if k in owner:
+                removed[c] = True
+                remap[c] = owner[k]
+            else:
+                owner[k] = c
+    before = np.cumsum(removed) - removed        # removed vertices before each concatenated position
+    gid = np.arange(voff[-1]) - before           # global id of a kept vertex
+    final = np.where(removed, gid[remap], gid)   # an owner is never removed
+    positions = np.concatenate([p for p, _, _ in shards])[~removed]
+    normals = np.concatenate([n for _, n, _ in shards])[~removed]
+    indices = np.concatenate([final[idx.astype(np.int64) + voff[s]] for s, (_, _, idx) in enumerate(shards)]).astype(np.uint32)
+    return positions, normals, indices
+
+
 def choose_split_level(init_factor: int, levels: int, world: int) -> int:
     """Coarse levels are refined redundantly on every rank; the split happens once the list is long enough that an
     equal-count split is also a balanced split of the final work (>= ~64 voxels per rank per SM is plenty), and
@@ -119,7 +169,7 @@ class ShardedRemesher:
             if self.rank == 0:
                 h.shard_reserve_welded(VS, T)          # before the key rows are extracted: a re-allocation would lose them
             # candidates: my welded vertices inside another shard's x range (equal keys are < 1.1e-5 apart; widened by 1e-4)
-            ivals = [(lo - 1e-4, hi + 1e-4) for r, (lo, hi) in enumerate(ranges) if r != self.rank and lo <= hi]
+            ivals = boundary_intervals(ranges, self.rank)
             kptr, kcnt = h.shard_boundary_keys(ivals)
             allk = torch.empty((self.world,), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(allk, torch.tensor([kcnt], dtype=torch.int64, device=dev))
