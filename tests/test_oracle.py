@@ -143,3 +143,21 @@ def test_oracle_equals_host_compiled_reference(oracle_mod):
     assert np.array_equal(bits(a), bits(ref.mesh_raw(vox, vs)))
     pts = np.load(G / "probe_points.npy")
     assert np.array_equal(bits(o.sdf(pts)), bits(ref.sd_obj(pts)))
+
+
+def test_oracle_port_matches_reference_at_baseline_config_c2(oracle_mod):
+    """BASELINE configs[1] (sd_obj, INIT 64 x 3 levels = 512^3) through the oracle PORT: every level's active list, the counts,
+    the index buffer, positions and normals hash to what the reference's own host-compiled kernels gave
+    (tools/gen_golden_fullsize.py -> golden_fullsize.json).  ~10 s on 8 cores."""
+    want = json.loads((G / "golden_fullsize.json").read_text())["cases"]["sd_obj_init64_l3"]
+    o = oracle_mod.Oracle(scenes.sd_obj())
+    vox, vs = o.create_voxel_field(5.0, 64)
+    assert h(oracle_mod, vox) == want["fnv_voxels_per_level"][0]
+    for lvl in range(3):
+        vox, vs = o.refine(vox, vs)
+        assert vox.shape[0] == want["level_counts"][lvl + 1]
+        assert h(oracle_mod, vox) == want["fnv_voxels_per_level"][lvl + 1]
+    tris, _ = o.mesh_raw(vox, vs)
+    pos, nrm, idx = o.weld(tris)
+    assert (idx.shape[0], pos.shape[0]) == (want["triangles"], want["vertices"])
+    assert h(oracle_mod, idx) == want["fnv_indices"] and h(oracle_mod, pos) == want["fnv_positions"] and h(oracle_mod, nrm) == want["fnv_normals"]
