@@ -1,20 +1,25 @@
 // sdm_kernels.cuh - the sm_100a kernels of the mesh-generation path.
 //
 //   k_init_field      level-0 dense list                       (src/cuda/mod.rs:105-122)
-//   k_refine          3x3x3 lattice classification + stable compaction of surviving children
-//                     (compute_mesh_generation.cu:12-62 + src/cuda/mod.rs:179-194)
-//   k_classify_edges  8 corner signs -> case index, triangle count/offsets (compute_mesh_generation.cu:77-86,
-//                     marching_cubes.cu:19-25); edge mid-points (marching_cubes.cu:13-16) de-duplicated by exact bit pattern
+//   k_refine          3x3x3 lattice signs per parent           (compute_mesh_generation.cu:12-62)
+//   k_refine_emit     stable compaction of surviving children, their case indices (:51, src/cuda/mod.rs:179-194)
+//   k_cases           8 corner signs -> case index (compute_mesh_generation.cu:77-86, marching_cubes.cu:19-23); only when the
+//                     last k_refine's lattice signs cannot be reused
+//   k_tri_offsets     triangle offsets per voxel from the case table (marching_cubes.cu:24-25)
+//   k_edges           edge mid-points (marching_cubes.cu:13-16) de-duplicated by exact bit pattern in a hash table
+//   k_uid_offsets / k_assign_uids   vertex ids in list order, start points
 //   k_project(+_tail) closest_surface_point per distinct mid-point (signed_distance.cu:227-240)
-//   k_build_masks     per-cell primitive masks for large scenes (exact culling of the fold)
-//   k_vertex_normals  empirical_normal per projected vertex (signed_distance.cu:181-202)
+//   k_build_masks(_fine)  per-cell primitive masks for large scenes (exact culling of the fold), zero-crossing flags
+//   k_vertex_normals  empirical_normal per projected vertex (signed_distance.cu:181-202) + the vertex's weld key
 //   k_orient          per triangle: face normal vs. centroid normal, flip (compute_mesh_generation.cu:103-113),
 //                     finite filter (src/cuda/mod.rs:289), first-occurrence slot per vertex
-//   k_weld_insert / k_weld_mark / k_bitscan / k_emit_*   the reference-order weld (src/cuda/mod.rs:263-296)
+//   k_weld_keys / k_weld_min / k_weld_mark / k_bitscan / k_emit_*   the reference-order weld (src/cuda/mod.rs:263-296)
 //   k_soup            the reference's raw 5-slot Triangle format (compute_mesh_generation.cu:107-118)
+//   k_shard_* / k_res_* / k_fix_*   multi-GPU: shard selection, distributed weld
 //
-// All kernels are persistent (grid = SMs x resident blocks) and read their problem sizes from DevState in
-// device memory, so that a whole remesh is enqueued without any host synchronisation.
+// All kernels read their problem sizes from DevState in device memory, so that a whole remesh is enqueued without any host
+// synchronisation.  A kernel that evaluates the SDF never waits for another block: every ordered step (compaction, offsets,
+// ids, ranks) is a streaming kernel of its own with a block-granular decoupled look-back.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
     float gx = 0.f, gy = 0.f, gz = 0.f;
     NewtonCycle cyc;
     cyc.start(0.f, 0.f, 0.f);
-    // Vertices are taken in chunks of consecutive ids (consecutive ids are spatial neighbours, k_classify_edges), one chunk
+    // Vertices are taken in chunks of consecutive ids (consecutive ids are spatial neighbours, k_uid_offsets), one chunk
     // per warp at a time: the lanes of a warp then work in one neighbourhood, which keeps the tile's primitive list short.
     // chunk size: large enough for coherence, small enough that every warp gets >= ~4 chunks (load balance)
     const uint32_t warps_in_grid = (gridDim.x * blockDim.x) >> 5;

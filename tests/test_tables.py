@@ -32,7 +32,7 @@ def test_packed_tables_decode_to_the_reference_tables(oracle_mod):
         assert packed[c] >> (12 * ntri[c]) == 0
     assert "%016x" % oracle_mod.fnv1a64(tri) == GOLD["mc_tables"]["fnv_triangle_int32"]
     assert "%016x" % oracle_mod.fnv1a64(np.asarray(corners, np.int32)) == GOLD["mc_tables"]["fnv_edge_int32"]
-    # the closed-form corner formulas used inside k_classify_edges
+    # the closed-form corner formulas used inside mc_edge_corners (k_edges / k_assign_uids)
     for e in range(12):
         c0 = (0 if e == 3 else e) if e < 4 else ((4 if e == 7 else e) if e < 8 else e - 8)
         c1 = (3 if e == 3 else e + 1) if e < 4 else ((7 if e == 7 else e + 1) if e < 8 else e - 4)
