@@ -330,6 +330,9 @@ int configure_kernels(SdmHandle* h) {
 // Per-cell primitive masks over the cube [-bb/2, bb/2]^3 (two levels: G/4 coarse cells prune for the G fine cells).
 int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     if (!h->mask_capable) { h->grid.enabled = 0; return SDM_OK; }
+    // The culling tests prove their drops with an absolute margin of 1e-4 against float rounding of distances (~3e-7 |d|):
+    // sound for the domains this path is used on (the reference's cube is 5 wide), not for arbitrarily large ones.
+    if (!(bb_size <= 32.0f)) return fail(SDM_ERR_INVALID, "scenes of more than 24 primitives need bb_size <= 32 (culling margins are absolute)");
     const uint32_t W = (h->scene_nprims + 31) / 32;
     uint32_t G = 16;
     while (G < init_factor && G < 128) G <<= 1;

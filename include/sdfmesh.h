@@ -83,7 +83,7 @@ typedef struct SdmPrimitive {      /* 40 B */
 
 /* Grid parameters; the reference compiles these in (bindings.h:9-10). */
 typedef struct SdmParams {
-    float bb_size;                 /* cube edge; level-0 grid spans [-bb/2, bb/2)^3 */
+    float bb_size;                 /* cube edge; level-0 grid spans [-bb/2, bb/2)^3; scenes of more than 24 primitives (culled fold): <= 32 */
     uint32_t init_factor;          /* level-0 voxels per axis */
     uint32_t levels;               /* refine steps performed by sdm_remesh */
 } SdmParams;
