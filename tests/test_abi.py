@@ -80,3 +80,23 @@ def test_obj_writer_layout(tmp_path):
     assert lines[7:9] == ["o default", "g default"] and lines[9] == "f 1/1/1 2/1/2 3/1/3"
     a = m.bevy_attributes()
     assert a["Indices::U32"].tolist() == [0, 1, 2] and a["ATTRIBUTE_POSITION"].shape == (3, 3)
+
+
+def test_header_is_plain_c_and_layouts_match_the_ctypes_mirrors(tmp_path):
+    """include/sdfmesh.h is the drop-in boundary: it must compile as C99 on its own, and every struct the Python mirror
+    (handler.py) passes across it must have the size the C compiler gives it."""
+    import subprocess
+
+    structs = {"SdmPoint": H._Point, "SdmVoxelField": H._VoxelField, "SdmParams": H._Params, "SdmMesh": H._Mesh, "SdmStats": H._Stats,
+               "SdmShardInfo": H._ShardInfo, "SdmShardBuffers": H._ShardBuffers, "SdmShardWeld": H._ShardWeld}
+    src = tmp_path / "layout.c"
+    body = "\n".join(f'    printf("{n} %zu\\n", sizeof({n}));' for n in structs)
+    src.write_text('#include <stdio.h>\n#include "sdfmesh.h"\nint main(void) {\n' + body +
+                   '\n    printf("SdmPrimitive %zu\\n", sizeof(SdmPrimitive));\n    printf("SdmTriangle %zu\\n", sizeof(SdmTriangle));\n    return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for n, c in structs.items():
+        assert int(out[n]) == ctypes.sizeof(c), f"{n}: C says {out[n]} bytes, ctypes mirror has {ctypes.sizeof(c)}"
+    assert int(out["SdmPrimitive"]) == bsdmg_b200.scenes.PRIM_DTYPE.itemsize == 40
+    assert int(out["SdmTriangle"]) == 72 and int(out["SdmPoint"]) == 12 and int(out["SdmVoxelField"]) == 32   # bindings.h:43-64
