@@ -121,70 +121,104 @@ def make_scene(name):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU baseline: bounded sample of the same workload through the host-compiled reference / the oracle port
+# CPU arm: the reference's own kernels, host-compiled, on a bounded sub-volume of the same workload
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_sampled_remesh(scene_name, scene, bb, init, levels, res, budget_s=15.0, seed=0):
-    """Sampled descent, entirely on the host: at every level a random sample of the surviving voxels is refined with
-    the reference's refine kernel (timed), which also gives the survival ratio; at the finest level a sample is meshed
-    with the reference's mesh kernel and welded (timed).  Per-level voxel counts and the whole-remesh time are
-    extrapolated linearly from the samples.  Uses oracle/_ref/libref_host.so (the reference's own kernels, host-compiled)
-    for the sd_obj scene, the oracle port otherwise; all host threads."""
-    from oracle import oracle as orc
+def host_threads() -> int:
+    """Threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1: ignored on purpose)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
-    use_ref = scene_name == "sd_obj" and orc.RefHost.available()
-    o = orc.Oracle(scene)
-    ref = orc.RefHost() if use_ref else None
-    threads = o.threads()
-    rng = np.random.default_rng(seed)
 
-    def refine_fn(v, s):
-        return ref.refine_raw(v, s) if use_ref else o.refine_raw(v, s)
+class CpuPath:
+    """The path on the host: refine kernel + stable retain per level, mesh kernel, weld - through oracle/_ref/libref_host.so
+    (kind "reference": the reference's kernels compiled unmodified for sd_obj, their functor templates over the reference's
+    own primitives for the other scenes, oracle/ref_functor.inc) or, where that library is absent, the oracle port."""
 
-    def mesh_fn(v, s):
-        return ref.mesh_raw(v, s) if use_ref else o.mesh_raw(v, s)[0]
+    def __init__(self, scene_name, scene):
+        from oracle import oracle as orc
 
-    def pick(lst, k):
-        if lst.shape[0] <= k:
-            return lst
-        return np.ascontiguousarray(lst[np.sort(rng.choice(lst.shape[0], k, replace=False))])
+        self.orc = orc
+        self.scene = scene
+        self.port = orc.Oracle(scene)
+        self.threads = host_threads()
+        orc.Oracle.set_threads(self.threads)
+        self.ref = orc.RefHost() if orc.RefHost.available() else None
+        self.kind = "reference" if self.ref is not None else "port"
+        if self.ref is not None:
+            self.ref.set_threads(self.threads)
+        self.mode = 0 if scene_name == "sd_obj" else (2 if scene_name == "mandelbulb" else 3)
 
-    vox, vs = o.create_voxel_field(bb, init)
-    est_count = float(vox.shape[0])
-    total = 0.0
-    parts = []
-    per_level_budget = budget_s * 0.35 / max(levels, 1)
-    for l in range(levels):
-        probe = pick(vox, 512)
-        t = time.perf_counter(); refine_fn(probe, vs); rate = probe.shape[0] / max(time.perf_counter() - t, 1e-6)
-        smp = pick(vox, int(max(4096, rate * per_level_budget)))
-        t = time.perf_counter(); raw = refine_fn(smp, vs); dt = time.perf_counter() - t
-        keep = np.isfinite(raw).all(axis=1)
-        children = raw[keep]
-        total += dt * est_count / smp.shape[0]
-        parts.append(f"refine L{l}: {smp.shape[0]} of ~{est_count:.0f} voxels in {dt:.2f}s")
-        est_count *= children.shape[0] / smp.shape[0]
-        vox, vs = np.ascontiguousarray(children), (vs / np.float32(2)).astype(np.float32)
+    def refine(self, vox, vs):
+        if self.ref is None:
+            raw = self.port.refine_raw(vox, vs)
+        elif self.mode == 0:
+            raw = self.ref.refine_raw(vox, vs)
+        else:
+            raw = self.ref.tpl_refine_raw(self.mode, self.scene, vox, vs)
+        keep = np.isfinite(raw).all(axis=1)                      # Vec::retain (src/cuda/mod.rs:192-193), stable
+        return np.ascontiguousarray(raw[keep]), (vs / np.float32(2)).astype(np.float32)
+
+    def mesh(self, vox, vs):
+        if self.ref is None:
+            tris = self.port.mesh_raw(vox, vs)[0]
+        elif self.mode == 0:
+            tris = self.ref.mesh_raw(vox, vs)
+        else:
+            tris = self.ref.tpl_mesh_raw(self.mode, self.scene, vox, vs)
+        return self.orc.Oracle.weld(tris)                          # src/cuda/mod.rs:263-296 (Rust host step, restated)
+
+    def remesh_cells(self, cells, vs, levels):
+        """The complete path on a sub-volume: the given level-0 voxels -> `levels` refinements -> mesh -> weld."""
+        vox = cells
+        for _ in range(levels):
+            if vox.shape[0] == 0:
+                break
+            vox, vs = self.refine(vox, vs)
         if vox.shape[0] == 0:
+            return 0, 0
+        pos, _, idx = self.mesh(vox, vs)
+        return int(idx.shape[0]), int(vox.shape[0])
+
+
+def cpu_subvolume_steps(scene_name, scene, bb, init, levels, res, steps, warmup, target_s=5.0):
+    """Each step = the COMPLETE path (all refinement levels, mesh kernel, weld) on a uniformly random subset of the level-0
+    voxels - a bounded sub-volume of the same workload - sized by a calibration probe so that one step takes ~target_s on
+    this host.  Effective samples of a step = (its share of the level-0 voxels) x res^3, the dense-grid equivalent the GPU
+    arm's metric uses; nothing is extrapolated inside a step, the step time is what was measured."""
+    cpu = CpuPath(scene_name, scene)
+    vox0, vs0 = cpu.port.create_voxel_field(bb, init)
+    n0 = vox0.shape[0]
+    rng = np.random.default_rng(2024)
+
+    def pick(k):
+        return np.ascontiguousarray(vox0[np.sort(rng.choice(n0, min(k, n0), replace=False))])
+
+    # calibration: grow the subset until it takes a measurable time, then scale to the target
+    k = min(n0, 64)
+    while True:
+        t = time.perf_counter(); cpu.remesh_cells(pick(k), vs0, levels); dt = time.perf_counter() - t
+        if dt >= 0.5 or k >= n0:
             break
-    tri_total = 0.0
-    if vox.shape[0]:
-        probe = pick(vox, 256)
-        t = time.perf_counter(); mesh_fn(probe, vs); rate = probe.shape[0] / max(time.perf_counter() - t, 1e-6)
-        smp = pick(vox, int(max(512, rate * budget_s * 0.6)))
-        t = time.perf_counter(); tris = mesh_fn(smp, vs); t_mesh = time.perf_counter() - t
-        t = time.perf_counter(); pos, nrm, idx = o.weld(tris); t_weld = time.perf_counter() - t
-        total += (t_mesh + t_weld) * est_count / smp.shape[0]
-        tri_total = idx.shape[0] * est_count / smp.shape[0]
-        parts.append(f"mesh kernel + weld: {smp.shape[0]} of ~{est_count:.0f} finest-level voxels in {t_mesh + t_weld:.2f}s")
+        k = min(n0, k * 4)
+    k = int(max(8, min(n0, k * target_s / max(dt, 1e-3))))
+    times, tris = [], []
+    for i in range(warmup + steps):
+        cells = pick(k)
+        t = time.perf_counter(); nt, _ = cpu.remesh_cells(cells, vs0, levels); dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt); tris.append(nt)
+    total = float(sum(times))
+    share = k / n0
+    eff = share * float(res) ** 3
     return {
-        "value": float(res) ** 3 / total,
-        "unit": "samples/s",
-        "cores": threads,
-        "kind": "reference" if use_ref else "port",
-        "sample": "sampled descent on the host; " + "; ".join(parts) + "; counts and times extrapolated linearly",
-        "extrapolated_s_per_remesh": total,
-        "estimated_finest_voxels": est_count,
-        "triangles_per_s": tri_total / total,
+        "value": eff * len(times) / total, "unit": "samples/s", "cores": cpu.threads, "kind": cpu.kind,
+        "sample": (f"each step = the complete path (level-0 voxels -> {levels} refinements -> mesh kernel -> weld) on {k} of {n0} level-0 voxels "
+                   f"(uniform random subset, 1/{n0 / k:.1f} of the domain); effective samples per step = {k}/{n0} x {res}^3; "
+                   f"a whole remesh at this rate would take {total / len(times) / share:.0f} s"),
+        "ms_per_step": total / len(times) * 1e3, "triangles_per_s": float(sum(tris)) / total,
+        "level0_voxels_per_step": k, "level0_voxels": n0, "whole_remesh_s_at_this_rate": total / len(times) / share,
     }
 
 
@@ -216,8 +250,13 @@ def main():
     res = init << levels
     scene = make_scene(scene_name)
     metric = f"effective SDF samples/s per full remesh @{res}^3"
+    from bsdmg_b200 import parallel as _par
+
     config = {"workload": args.workload, "description": desc, "scene": scene_name, "primitives": int(scene.shape[0]),
-              "bb_size": bb, "init_factor": init, "levels": levels, "resolution": res}
+              "bb_size": bb, "init_factor": init, "levels": levels, "resolution": res,
+              "l2": "every step clears >0.3 GB of tables / bitmaps and rewrites all intermediates (working set > 126 MB L2); no separate flush",
+              "parallelism": (f"x-slab shards of the level-{_par.choose_split_level(init, levels, max(world, args.gpus))} active list over {max(world, args.gpus)} GPU(s), "
+                              "welded where they are made, interface keys resolved and shards assembled on rank 0 (NCCL)") if max(world, args.gpus) > 1 else "1 GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -302,7 +341,8 @@ def main():
         # dominant SDF kernel: achieved = (primitive, point) distance evaluations it actually folded (device counters, after
         # culling) x algorithmic FP32 ops per such evaluation (scene average) / its CUDA-event time
         pe = st["prim_evals"]
-        stage_of = {"k_refine": "refine", "k_cases+k_tri_offsets": "classify", "k_project": "project", "k_vertex_normals": "normals", "k_orient": "orient"}
+        stage_of = {"k_refine": "refine", "k_cases+k_tri_offsets": "classify", "k_project": "project", "k_project_tail": "tail",
+                    "k_vertex_normals": "normals", "k_orient": "orient"}
         cand = {k: v for k, v in kavg.items() if k in stage_of}
         top = max(cand, key=cand.get)
         nprims_compiled = sum(12 if int(p["kind"]) == 3 else 1 for p in scene)
@@ -324,6 +364,16 @@ def main():
                             "peak_source": peak_src,
                             "algorithmic_bytes": emit_bytes}
 
+    # ---- checksum of the mesh the timed loop produced (outside the timed region): FNV-1a-64 of the raw bytes, the checksum of
+    #      tests/golden; identical at every N because the merged mesh is byte-identical to the single-GPU mesh
+    mesh_fnv = None
+    if rank == 0 and runner.mesh is not None:
+        mm = h._download(runner.mesh)
+        lib = bsdmg_b200.load_library()
+        fnv = lambda a: "%016x" % int(lib.sdm_hash_bytes(a.ctypes.data, a.nbytes))
+        mesh_fnv = {"indices": fnv(mm.indices), "positions": fnv(mm.positions), "normals": fnv(mm.normals)}
+        del mm
+
     # ---- end-to-end arm: host scene in, pinned host mesh out, every step ------------------------------------------
     e2e = runner.e2e(scene, args.steps, max(args.warmup, 3), barrier)
     if dist is not None:
@@ -336,11 +386,12 @@ def main():
             "metric": metric, "value": float(res) ** 3 * args.steps / elapsed, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic procedural scene (analytic SDF); no dataset",
-            "config": dict(config, l2="every step clears >0.5 GB of hash tables and rewrites all intermediates (working set > 126 MB L2); no separate flush",
-                           parallelism=f"x-slab shards of the level-{runner.split_level} active list over {world} GPU(s), mesh shards gathered to rank 0 (NCCL)" if world > 1 else "1 GPU"),
-            "triangles_per_s": tri_count * args.steps / elapsed, "triangles": tri_count, "vertices": vert_count,
+            "config": config,
+            "triangles_per_s": tri_count * args.steps / elapsed, "triangles": tri_count, "vertices": vert_count, "mesh_fnv": mesh_fnv,
             "gpu_ms_per_step": gpu_ms / args.steps, "sdf_evals_per_step": st["sdf_evals"], "sdf_evals_per_s": st["sdf_evals"] * args.steps / elapsed,
             "level_counts": st["level_counts"][: levels + 1], "prim_point_evals_per_step": st["prim_evals"], "gpu_launches": launches, "clocks": clocks,
+            "newton": {"iterations": st["newton_iterations"], "stragglers": st["stragglers"], "escaped_vertices": st["escaped_vertices"],
+                       "list_fallback_tiles": st["list_fallback_tiles"]},
             "e2e": {"value": float(res) ** 3 * args.steps / e2e["elapsed"], "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["elapsed"] * 1e3 / args.steps},
             "kernel_ms": {k: round(v, 5) for k, v in kavg.items()},
@@ -350,7 +401,8 @@ def main():
             line["rank0_phase_ms"] = dict(zip(("local_shard_and_weld", "counts_ranges_boundary_keys", "resolve", "gather"), getattr(runner, "last_phases", [])))
             line["root_weld_fallback"] = bool(getattr(runner, "last_fallback", False))
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_sampled_remesh(scene_name, scene, bb, init, levels, res)
+            cb = cpu_subvolume_steps(scene_name, scene, bb, init, levels, res, steps=3, warmup=0, target_s=5.0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "triangles_per_s")}
         print(json.dumps(line), flush=True)
     h.close()
     if dist is not None:
@@ -391,24 +443,22 @@ def run_animated(args, bb, init, levels, res, config):
 
 
 def run_reference(args, scene_name, scene, bb, init, levels, res, metric, config):
-    """--impl reference: the reference's own CPU code path for this workload (oracle/_ref for sd_obj, else the oracle
-    port), all host threads; each step is one bounded sampled remesh (cpu_sampled_remesh) extrapolated to a full one."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/libref_host.so: its kernels compiled
+    for the host, all host threads) on this arm's workload, metric and unit.  Every one of the --steps K timed steps (after
+    --warmup W) is a bounded sample of the workload: the complete path on a random sub-volume sized to ~5 s, so that
+    `ms_per_step` x steps is the time this run really takes."""
     from oracle import oracle as orc
 
     orc.build()
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    results = [cpu_sampled_remesh(scene_name, scene, bb, init, levels, res, budget_s=12.0, seed=i) for i in range(warm + steps)]
-    r = results[-1]
-    value = float(np.mean([x["value"] for x in results[-steps:]]))
+    r = cpu_subvolume_steps(scene_name, scene, bb, init, levels, res, steps=max(1, args.steps), warmup=max(0, args.warmup), target_s=5.0)
     line = {
-        "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": float(res) ** 3 / value * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic procedural scene (analytic SDF); no dataset", "config": config,
+        "impl": "reference", "metric": metric, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": max(1, args.steps),
+        "warmup": max(0, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic procedural scene (analytic SDF); no dataset", "config": config,
         "triangles_per_s": r["triangles_per_s"],
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
-        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "whole_remesh_s_at_this_rate": r["whole_remesh_s_at_this_rate"], "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 

@@ -74,7 +74,7 @@ __device__ __forceinline__ SceneView build_sd_obj(SdObjScene* s) {
     __syncthreads();
     SceneView v;
     v.prims = s->prims; v.runs = s->runs; v.nruns = 2; v.nprims = 13;
-    v.wmask = nullptr; v.W = 0; v.tcand = nullptr; v.tlist = nullptr; v.tcount = nullptr;
+    v.wmask = nullptr; v.W = 0; v.tlist = nullptr; v.tcount = nullptr;
     return v;
 }
 

@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "sdm_kernels.cuh"
 
 // Device-side clears go through a kernel (one engine for everything on the compute stream; the copy engines are left to the
@@ -74,10 +76,26 @@ template <class T> struct DevBuf {   // grow-only, like DynamicCudaSlice::get_or
         p = nullptr; n = 0;
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
         if (e == cudaSuccess) n = want;
+        else { p = nullptr; (void) cudaGetLastError(); }   // do not leave the allocation failure behind as a sticky "last error"
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
+// temporary device buffer of one call: freed on every return path
+template <class T> struct TempBuf {
+    T* p = nullptr;
+    cudaError_t alloc(size_t count) {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; (void) cudaGetLastError(); }
+        return e;
+    }
+    ~TempBuf() { if (p) cudaFree(p); }
+    TempBuf() = default;
+    TempBuf(const TempBuf&) = delete;
+    TempBuf& operator=(const TempBuf&) = delete;
+};
+
+uint32_t grown(uint32_t cap) { return (uint32_t) std::min<uint64_t>((uint64_t) cap * 2, 1ull << 30); }
 
 uint32_t pow2_at_least(uint64_t v) {
     uint64_t p = 1;
@@ -214,9 +232,21 @@ struct SdmHandle {
     uint32_t cap_tris = 0, cap_uniq = 0, table_entries = 0;
     DevBuf<uint8_t> cases;
     DevBuf<uint32_t> m27;              // per parent: the 27 lattice signs of the last k_refine
-    DevBuf<uint32_t> uid_base;         // per voxel: id of the first vertex it created
-    DevBuf<uint16_t> won;              // per voxel: edges whose vertex-table entry this voxel created
     DevBuf<uint32_t> entry_uid;        // per vertex-table entry: the id of its vertex
+    // Inherited primitive lists (culled scenes): vl[a] = one record per voxel of the level refined last (its own need-list,
+    // k_refine), vl[a ^ 1] = the records of the level before; vparent[b] = record index (= parent) of every voxel of the
+    // current level.  lists_level = level whose voxels have a valid vparent (-1: none, the kernels use the cell masks).
+    DevBuf<uint4> vl[2];
+    DevBuf<uint32_t> vparent[2];
+    int vl_cur = 0, vp_cur = 0, lists_level = -1;
+    float list_delta = 0.0f;           // inflation of the boxes the current records are proven on (= slack of the mesh stage)
+    float delta_override = 0.0f;       // > 0: sdm_remesh knows the final voxel size and uses one inflation for all levels
+    DevBuf<uint32_t> urec, tri_rec;    // per vertex / per raw triangle: its list record
+    DevBuf<uint32_t> uesc;             // bitmap: vertices that ended outside their record's region
+    EdgeLattice lattice {};            // integer lattice of the current field (k_edges' fast keys); enabled = 0: generic keys
+    bool lattice_ok = true;            // cleared when a mesh stage reported ERR_LATTICE for the current field
+    float field_bb = 0.0f, lat_fail_bb = -1.0f;   // domain of the current field / the one whose grid turned out not to be a lattice
+    uint32_t field_init = 0, lat_fail_init = 0;
     DevBuf<uint32_t> vidx;             // per vertex: its index in the welded output
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
     DevBuf<float> ustart, upos, unrm;
@@ -228,7 +258,7 @@ struct SdmHandle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_mesh_done[2] = { nullptr, nullptr }, ev_copy_done[2] = { nullptr, nullptr };
     DevBuf<uint4> table1, table2;
-    DevBuf<uint64_t> tiles, tiles2;
+    DevBuf<uint64_t> tiles;
     DevBuf<Straggler> stragglers;
     uint32_t cap_stragglers = 0;
     uint32_t cases_epoch = 0;           // epoch passed to that k_refine (DevState::cases_from_refine)
@@ -250,6 +280,9 @@ struct SdmHandle {
 
     // persistent grid sizes
     int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0, g_edges = 0;
+    uint32_t proj_chunk = 256;          // vertex chunk per warp in k_project (SDM_PROJ_CHUNK overrides)
+    float slack_factor = 1.0f;         // inflation of the list regions in units of the child voxel size (SDM_SLACK overrides)
+    bool use_lists = true, use_lattice = true;   // SDM_NO_LISTS / SDM_NO_LATTICE: developer switches for A/B measurements
 
     SdmStats stats {};
 
@@ -271,6 +304,20 @@ size_t smem_for(const SdmHandle* h, int threads = 256, bool staged = false) {
     else b = (size_t) h->scene_bytes;
     return (b + 15) & ~(size_t) 15;
 }
+
+// NVTX ranges per remesh, level and stage (the reference has them on its render path only,
+// src/cuda/mod.rs:354-408).  Header-only NVTX3: a no-op unless a tool (nsys / ncu --nvtx) is attached.
+struct NvtxRange {
+    NvtxRange(const SdmHandle*, const char* name, int index = -1) {
+        if (index < 0) { nvtxRangePushA(name); return; }
+        char buf[64];
+        snprintf(buf, sizeof buf, "%s %d", name, index);
+        nvtxRangePushA(buf);
+    }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // profiling: mark(h, name) closes the interval that started at the previous mark
 void prof_begin(SdmHandle* h) {
@@ -321,7 +368,7 @@ int configure_kernels(SdmHandle* h) {
     h->g_light = h->num_sms * 8;
     {   // static-shared-memory kernels of the classification stage
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edges, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edges<true>, 256, 0));
         h->g_edges = std::max(per_sm, 1) * h->num_sms;
     }
     return SDM_OK;
@@ -368,49 +415,69 @@ int ensure_masks(SdmHandle* h, float bb_size, uint32_t init_factor) {
     return SDM_OK;
 }
 
+// All buffers that scale with the voxel capacity.  The capacities in the handle are committed only after every allocation
+// has succeeded; if one fails (DevBuf::reserve has already freed the old buffer) they are zeroed, so that the next call
+// re-allocates instead of launching kernels bounded by capacities that no buffer has.
+int reserve_all(SdmHandle* h, uint32_t cap_vox, uint32_t cap_tris, uint32_t cap_uniq, uint32_t table_entries) {
+    for (int i = 0; i < 2; i++) CK(h->vox[i].reserve((size_t) cap_vox * 3));
+    CK(h->cases.reserve((size_t) cap_vox + 4));
+    for (int i = 0; i < 2; i++) { CK(h->vl[i].reserve((size_t) cap_vox * 2)); CK(h->vparent[i].reserve(cap_vox)); }
+    CK(h->tri_rec.reserve(cap_tris));
+    CK(h->urec.reserve(cap_uniq));
+    CK(h->uesc.reserve((size_t) cap_uniq / 32 + 32));
+    CK(h->m27.reserve(cap_vox));
+    CK(h->tri_off.reserve(cap_vox));
+    CK(h->slot_ref.reserve((size_t) cap_tris * 3));
+    CK(h->tri_uid.reserve((size_t) cap_tris * 3));
+    for (int b = 0; b < 2; b++) CK(h->out_idx[b].reserve((size_t) cap_tris * 3));
+    CK(h->first_bits.reserve(((size_t) cap_tris * 3 + 31) / 32 + 32));
+    CK(h->first_prefix.reserve(((size_t) cap_tris * 3 + 31) / 32 + 32));
+    CK(h->tri_valid_bits.reserve(((size_t) cap_tris + 31) / 32 + 32));
+    CK(h->tri_prefix.reserve(((size_t) cap_tris + 31) / 32 + 32));
+    CK(h->first_slot.reserve(cap_uniq));
+    CK(h->wref.reserve(cap_uniq));
+    CK(h->vidx.reserve(cap_uniq));
+    CK(h->ustart.reserve((size_t) cap_uniq * 3));
+    CK(h->upos.reserve((size_t) cap_uniq * 3));
+    CK(h->unrm.reserve((size_t) cap_uniq * 3));
+    for (int b = 0; b < 2; b++) { CK(h->out_pos[b].reserve((size_t) cap_uniq * 3)); CK(h->out_nrm[b].reserve((size_t) cap_uniq * 3)); }
+    CK(h->table1.reserve(table_entries));
+    CK(h->entry_uid.reserve(table_entries));
+    CK(h->table2.reserve(table_entries));
+    const size_t max_tiles = std::max<size_t>(((size_t) cap_tris * 3 / 32 + 31) / 32, (size_t) cap_vox / 32) + 64;
+    const size_t old_tiles = h->tiles.n;
+    CK(h->tiles.reserve(max_tiles));
+    if (h->tiles.n != old_tiles) CK(dev_fill(h->stream, h->tiles.p, 0, h->tiles.n * sizeof(uint64_t)));
+    CK(h->stragglers.reserve(cap_uniq / 8 + 4096));
+    return SDM_OK;
+}
+
 int ensure_capacity(SdmHandle* h, uint32_t cap_vox) {
     if (cap_vox <= h->cap_vox) return SDM_OK;
     if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));   // no download may be reading a buffer that is about to move
     // copy-preserving growth of the current list is not needed: callers re-create the field after growing
-    h->cap_vox = cap_vox;
-    h->cap_tris = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 3, 0x3FFFFFFFull);   // < 2^32 / 3 slots
-    h->cap_uniq = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 2, 0x7FFFFFFFull);
-    h->table_entries = pow2_at_least((uint64_t) h->cap_uniq * 2);
-    for (int i = 0; i < 2; i++) CK(h->vox[i].reserve((size_t) cap_vox * 3));
-    CK(h->cases.reserve((size_t) cap_vox + 4));
-    CK(h->won.reserve((size_t) cap_vox + 4));
-    CK(h->uid_base.reserve((size_t) cap_vox + 4));
-    CK(h->m27.reserve(cap_vox));
-    CK(h->tri_off.reserve(cap_vox));
-    CK(h->slot_ref.reserve((size_t) h->cap_tris * 3));
-    CK(h->tri_uid.reserve((size_t) h->cap_tris * 3));
-    for (int b = 0; b < 2; b++) CK(h->out_idx[b].reserve((size_t) h->cap_tris * 3));
-    CK(h->first_bits.reserve(((size_t) h->cap_tris * 3 + 31) / 32 + 32));
-    CK(h->first_prefix.reserve(((size_t) h->cap_tris * 3 + 31) / 32 + 32));
-    CK(h->tri_valid_bits.reserve(((size_t) h->cap_tris + 31) / 32 + 32));
-    CK(h->tri_prefix.reserve(((size_t) h->cap_tris + 31) / 32 + 32));
-    CK(h->first_slot.reserve(h->cap_uniq));
-    CK(h->wref.reserve(h->cap_uniq));
-    CK(h->vidx.reserve(h->cap_uniq));
-    CK(h->ustart.reserve((size_t) h->cap_uniq * 3));
-    CK(h->upos.reserve((size_t) h->cap_uniq * 3));
-    CK(h->unrm.reserve((size_t) h->cap_uniq * 3));
-    for (int b = 0; b < 2; b++) { CK(h->out_pos[b].reserve((size_t) h->cap_uniq * 3)); CK(h->out_nrm[b].reserve((size_t) h->cap_uniq * 3)); }
-    CK(h->table1.reserve(h->table_entries));
-    CK(h->entry_uid.reserve(h->table_entries));
-    CK(h->table2.reserve(h->table_entries));
-    const size_t max_tiles = std::max<size_t>(((size_t) h->cap_tris * 3 / 32 + 31) / 32, (size_t) cap_vox / 32) + 64;
-    const size_t old_tiles = h->tiles.n;
-    CK(h->tiles.reserve(max_tiles));
-    if (h->tiles.n != old_tiles) CK(dev_fill(h->stream, h->tiles.p, 0, h->tiles.n * sizeof(uint64_t)));
-    const size_t old_tiles2 = h->tiles2.n;
-    CK(h->tiles2.reserve((size_t) cap_vox / 32 + 64));
-    if (h->tiles2.n != old_tiles2) CK(dev_fill(h->stream, h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t)));
-    h->cap_stragglers = h->cap_uniq / 8 + 4096;
-    CK(h->stragglers.reserve(h->cap_stragglers));
-    h->table1_entries = h->table_entries;
+    const uint32_t cap_tris = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 3, 0x3FFFFFFFull);   // < 2^32 / 3 slots
+    const uint32_t cap_uniq = (uint32_t) std::min<uint64_t>((uint64_t) cap_vox * 2, 0x7FFFFFFFull);
+    const uint32_t table_entries = pow2_at_least((uint64_t) cap_uniq * 2);
     h->have_field = false;
     h->mesh_valid = false;
+    const int rc = reserve_all(h, cap_vox, cap_tris, cap_uniq, table_entries);
+    if (rc) {
+        h->cap_vox = h->cap_tris = h->cap_uniq = h->table_entries = h->table1_entries = h->cap_stragglers = 0;
+        return rc;
+    }
+    h->cap_vox = cap_vox; h->cap_tris = cap_tris; h->cap_uniq = cap_uniq; h->table_entries = table_entries;
+    h->cap_stragglers = cap_uniq / 8 + 4096;
+    h->table1_entries = h->table_entries;
+    return SDM_OK;
+}
+
+// capacity (a doubling of the current one) that holds n0 level-0 voxels; the lists are limited to 2^30 voxels
+int capacity_for(SdmHandle* h, uint64_t n0, uint32_t* want) {
+    if (n0 > (1ull << 30)) return fail(SDM_ERR_CAPACITY, "more than 2^30 voxels in one list");
+    uint32_t w = std::max(h->cap_vox, 1u << 21);
+    while (w < n0) w = grown(w);
+    *want = w;
     return SDM_OK;
 }
 
@@ -418,7 +485,6 @@ uint32_t next_epoch(SdmHandle* h) {
     h->epoch++;
     if (h->epoch >= (1u << 30)) {   // wrap: make every stale descriptor invalid again
         dev_fill(h->stream, h->tiles.p, 0, h->tiles.n * sizeof(uint64_t));
-        dev_fill(h->stream, h->tiles2.p, 0, h->tiles2.n * sizeof(uint64_t));
         h->epoch = 1;
     }
     return h->epoch;
@@ -448,6 +514,12 @@ int enqueue_init_field(SdmHandle* h, const SdmParams& p) {
     h->voxel_size[0] = h->voxel_size[1] = h->voxel_size[2] = size;
     h->have_field = true;
     h->mesh_valid = false;
+    h->lists_level = -1;
+    // the field's lattice: origin = min corner of the domain; the unit (half a voxel) follows the voxel size at mesh time
+    h->lattice.ox = h->lattice.oy = h->lattice.oz = 0.0f - p.bb_size / 2.0f;
+    h->lattice.enabled = 1;
+    h->field_bb = p.bb_size; h->field_init = p.init_factor;
+    h->lattice_ok = !(p.bb_size == h->lat_fail_bb && p.init_factor == h->lat_fail_init);
     return SDM_OK;
 }
 
@@ -457,11 +529,23 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     int mrc = ensure_masks_any(h);
     if (mrc) return mrc;
     const float ox = h->voxel_size[0] / 2.0f, oy = h->voxel_size[1] / 2.0f, oz = h->voxel_size[2] / 2.0f;   // :20
+    // Inherited lists (culled scenes): this level's parents get their own records (vl[vl_cur ^ 1]), proven on their boxes inflated
+    // by delta; candidates come from the records they inherited (vl[vl_cur] through vparent[vp_cur]) when there are any.
+    // Level 0 is dense: a tile's 32 parents are 32 different cells, and inflating them would pull the rows of ~300 cells into the
+    // tile's candidates.  Records start at level 1 (whose parents take their candidates from the cell masks once more).
+    const bool lists = h->mask_capable && h->grid.enabled && h->use_lists && h->grid.W <= 32 && h->level >= 1;
+    const bool inherit = lists && h->lists_level == h->level;
+    const float delta = lists ? (h->delta_override > 0.0f ? h->delta_override : h->slack_factor * std::max(ox, std::max(oy, oz))) : 0.0f;
+    NvtxRange nv(h, "refine level", h->level);
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p,
-                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, h->level == 0 && h->grid.enabled ? 1 : 0);
+                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, h->level == 0 && h->grid.enabled ? 1 : 0,
+                                                                inherit ? h->vl[h->vl_cur].p : nullptr, inherit ? h->vparent[h->vp_cur].p : nullptr,
+                                                                lists ? h->vl[h->vl_cur ^ 1].p : nullptr, delta);
     mark(h, "k_refine");
     k_refine_emit<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cap_vox,
-                                                     ox, oy, oz, h->m27.p, with_cases ? h->cases.p : nullptr);
+                                                     ox, oy, oz, h->m27.p, with_cases ? h->cases.p : nullptr, lists ? h->vparent[h->vp_cur ^ 1].p : nullptr);
+    if (lists) { h->vl_cur ^= 1; h->vp_cur ^= 1; h->lists_level = h->level + 1; h->list_delta = delta; }
+    else h->lists_level = -1;
     h->cases_for_level = with_cases ? h->level + 1 : -1;
     mark(h, "k_refine_emit");
     h->stats.kernel_launches += 2;
@@ -474,7 +558,7 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
 // clears sized on the device from n_uniq / n_tris_raw (which must already be in DevState)
 int enqueue_weld_clears(SdmHandle* h, bool clear_first_slot) {
     k_clear_weld_state<<<h->g_light, 256, 0, h->stream>>>(h->state.p, h->first_slot.p, h->first_bits.p, h->table2.p, h->table_entries,
-                                                          h->cap_uniq, clear_first_slot ? 1 : 0);
+                                                          h->cap_uniq, clear_first_slot ? 1 : 0, clear_first_slot ? h->uesc.p : nullptr);
     h->stats.kernel_launches++;
     return SDM_OK;
 }
@@ -489,41 +573,64 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     cudaStream_t s = h->stream;
     // the mesh stage may be re-run on the same field: reset the mesh-stage counters and tickets only (not error_flags)
     k_reset_mesh_state<<<1, 32, 0, s>>>(h->state.p);
-    // vertex de-duplication table: sized from the previous mesh of this handle (4x its vertex count), full size at first;
-    // an overflow is detected (ERR_HASH_FULL) and retried with the full table
-    CK(dev_fill(s, h->table1.p, 0xFF, (size_t) h->table1_entries * 16));
+    // Vertex de-duplication table: sized from the previous mesh of this handle (4x its vertex count), full size at first; an
+    // overflow is detected (ERR_HASH_FULL) and retried with the full table.  Fast path: 8-byte lattice keys (0 = empty).
+    const bool lat = h->use_lattice && h->lattice.enabled && h->lattice_ok;
+    EdgeLattice L = h->lattice;
+    L.hx = sx / 2.0f; L.hy = sy / 2.0f; L.hz = sz / 2.0f;
+    L.ihx = 1.0f / L.hx; L.ihy = 1.0f / L.hy; L.ihz = 1.0f / L.hz;
+    CK(dev_fill(s, h->table1.p, lat ? 0x00 : 0xFF, (size_t) h->table1_entries * (lat ? 8 : 16)));
     mark(h, "clears");
-    k_cases<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, h->cases.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? h->cases_epoch : 0u);
-    k_tri_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->cases.p, h->tri_off.p, next_epoch(h), h->tiles.p, h->cap_tris);
-    mark(h, "k_cases+k_tri_offsets");
-    k_edges<<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->won.p, sx, sy, sz);
-    mark(h, "k_edges");
-    k_uid_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->won.p, h->uid_base.p, next_epoch(h), h->tiles2.p, h->cap_uniq);
-    k_assign_uids<<<h->g_light * 2, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->won.p, h->uid_base.p, h->entry_uid.p, h->slot_ref.p,
-                                                h->ustart.p, sx, sy, sz);
-    mark(h, "k_assign_uids");
-    h->stats.kernel_launches += 4;
+    const bool lists = h->mask_capable && h->use_lists && h->lists_level == h->level && h->grid.W <= 32;
+    const uint4* vl = lists ? h->vl[h->vl_cur].p : nullptr;
+    const uint32_t* vparent = lists ? h->vparent[h->vp_cur].p : nullptr;
+    const float slack2 = h->list_delta * h->list_delta;
+    {
+        NvtxRange nv(h, "mesh: classify + edge vertices");
+        k_cases<<<h->g_classify, 256, smem, s>>>(h->scene.p, vox, h->state.p, h->level, h->cases.p, sx, sy, sz, h->grid, h->cases_for_level == h->level ? h->cases_epoch : 0u);
+        k_tri_offsets<<<h->g_light, 256, 0, s>>>(h->state.p, h->level, h->cases.p, h->tri_off.p, next_epoch(h), h->tiles.p, h->cap_tris);
+        mark(h, "k_cases+k_tri_offsets");
+        if (lat)
+            k_edges<true><<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->tri_rec.p,
+                                                     vparent, h->entry_uid.p, h->ustart.p, h->urec.p, L, sx, sy, sz, h->cap_uniq);
+        else
+            k_edges<false><<<h->g_edges, 256, 0, s>>>(vox, h->state.p, h->level, h->cases.p, h->tri_off.p, h->table1.p, h->table1_entries - 1, h->slot_ref.p, h->tri_rec.p,
+                                                      vparent, h->entry_uid.p, h->ustart.p, h->urec.p, L, sx, sy, sz, h->cap_uniq);
+        mark(h, "k_edges");
+        h->stats.kernel_launches += 3;
+    }
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
-    k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid,
-                                                 256u);   // vertex chunk per warp (B200 sweep with per-lane culling: 64: 3.82, 128: 3.44, 256: 3.38, 512: 3.59, 1024: 4.08 ms)
-    mark(h, "k_project");
-    k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid);
-    mark(h, "k_project_tail");
-    k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid,
-                                                        fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p);
-    mark(h, "k_vertex_normals");
-    k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
-                                                h->tri_valid_bits.p, h->grid);
-    mark(h, "k_orient");
-    h->stats.kernel_launches += 5;
+    {
+        NvtxRange nv(h, "mesh: project");
+        k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid,
+                                                     h->proj_chunk, vl, h->urec.p, h->uesc.p, slack2);
+        mark(h, "k_project");
+        k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid, h->ustart.p,
+                                                       vl ? h->uesc.p : nullptr, slack2);
+        mark(h, "k_project_tail");
+    }
+    {
+        NvtxRange nv(h, "mesh: vertex normals + weld keys");
+        k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid,
+                                                            fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p, vl, h->urec.p, h->uesc.p);
+        mark(h, "k_vertex_normals");
+    }
+    {
+        NvtxRange nv(h, "mesh: orient");
+        k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
+                                                    h->tri_valid_bits.p, h->grid, vl, h->tri_rec.p, h->uesc.p);
+        mark(h, "k_orient");
+    }
+    h->stats.kernel_launches += 6;
     CK(cudaGetLastError());
     return SDM_OK;
 }
 
 // the reference-order weld over (upos, unrm, tri_uid, first_slot, tri_valid_bits) and the counters in DevState
 int enqueue_weld(SdmHandle* h, bool keys_inserted) {
+    NvtxRange nv(h, "weld + emit");
     cudaStream_t s = h->stream;
     const int b = h->out_sel;
     CK(cudaStreamWaitEvent(s, h->ev_copy_done[b], 0));   // the download of the mesh that used this set two remeshes ago
@@ -576,6 +683,10 @@ void fill_stats(SdmHandle* h, bool meshed) {
     if (meshed) evals += 8ull * st.level_count[h->level] + 13ull * st.newton_iters + 12ull * st.n_uniq + 12ull * st.n_tris_raw;
     h->stats.sdf_evals = evals;
     for (int i = 0; i < 6; i++) h->stats.prim_evals[i] = st.prim_evals[i];
+    if (meshed) {
+        h->stats.escaped_vertices = st.n_escaped; h->stats.list_fallback_tiles = st.list_fallbacks;
+        h->stats.stragglers = st.n_stragglers; h->stats.newton_iterations = st.newton_iters;
+    }
 }
 
 void mesh_view(SdmHandle* h, SdmMesh* m) {
@@ -591,12 +702,10 @@ void mesh_view(SdmHandle* h, SdmMesh* m) {
 }
 
 int check_params(const SdmParams& p) {
-    if (!(p.bb_size > 0.0f) || p.init_factor == 0 || p.init_factor > 2048 || p.levels > 15)
+    if (!(p.bb_size > 0.0f) || p.init_factor == 0 || p.init_factor > 1024 || p.levels > 15)
         return fail(SDM_ERR_INVALID, "bad SdmParams");
     return SDM_OK;
 }
-
-uint32_t grown(uint32_t cap) { return (uint32_t) std::min<uint64_t>((uint64_t) cap * 2, 1ull << 30); }
 
 // after a successful mesh: size the vertex table of the next mesh from this one
 void adapt_table1(SdmHandle* h) {
@@ -606,6 +715,8 @@ void adapt_table1(SdmHandle* h) {
 // the adaptive vertex table was too small (and nothing else overflowed): retry with the full table, same capacities
 bool only_table1_overflow(SdmHandle* h, uint32_t flags) {
     if (flags == ERR_HASH_FULL && h->table1_entries < h->table_entries) { h->table1_entries = h->table_entries; return true; }
+    // a voxel off the integer lattice (non-dyadic grid): same capacities, generic float-bit keys from now on for this field
+    if (flags == ERR_LATTICE && h->lattice_ok) { h->lattice_ok = false; h->lat_fail_bb = h->field_bb; h->lat_fail_init = h->field_init; return true; }
     return false;
 }
 
@@ -683,6 +794,10 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         cudaMemcpyToSymbolAsync(c_mc_edgemask, SDM_MC_EDGEMASK_INIT, sizeof(SDM_MC_EDGEMASK_INIT), 0, cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyToSymbolAsync(c_mc_ntri, SDM_MC_NTRI_INIT, sizeof(SDM_MC_NTRI_INIT), 0, cudaMemcpyHostToDevice, h->stream);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, std::string("init: ") + cudaGetErrorString(cudaGetLastError())); break; }
+        if (const char* e = getenv("SDM_SLACK")) { const float v = (float) atof(e); if (v > 0.0f && v <= 8.0f) h->slack_factor = v; }
+        if (const char* e = getenv("SDM_PROJ_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->proj_chunk = (uint32_t) v & ~31u; }
+        h->use_lists = getenv("SDM_NO_LISTS") == nullptr;
+        h->use_lattice = getenv("SDM_NO_LATTICE") == nullptr;
         SdmPrimitive def[2];
         sdm_scene_default(def, 2);
         rc = sdm_set_scene(h, def, 2);
@@ -705,7 +820,9 @@ void sdm_destroy(SdmHandle* h) {
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
     h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
-    h->won.release(); h->entry_uid.release(); h->vidx.release(); h->uid_base.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release(); h->tiles2.release(); h->stragglers.release(); h->state.release();
+    h->entry_uid.release(); h->vidx.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release();
+    for (int i = 0; i < 2; i++) { h->vl[i].release(); h->vparent[i].release(); }
+    h->urec.release(); h->tri_rec.release(); h->uesc.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     if (h->host_scratch) cudaFreeHost(h->host_scratch);
@@ -723,11 +840,13 @@ static int eval_common(SdmHandle* h, const float* points, uint32_t n, float* out
     if (!h || !points || !out) return fail(SDM_ERR_INVALID, "null argument");
     if (n == 0) return SDM_OK;
     CK(cudaSetDevice(h->device));
-    float *d_in = nullptr, *d_out = nullptr;
-    uint32_t* d_it = nullptr;
-    CK(cudaMalloc(&d_in, (size_t) n * 12));
-    CK(cudaMalloc(&d_out, (size_t) n * 4 * width));
-    if (iters) CK(cudaMalloc(&d_it, (size_t) n * 4));
+    TempBuf<float> t_in, t_out;
+    TempBuf<uint32_t> t_it;
+    CK(t_in.alloc((size_t) n * 3));
+    CK(t_out.alloc((size_t) n * width));
+    if (iters) CK(t_it.alloc(n));
+    float *d_in = t_in.p, *d_out = t_out.p;
+    uint32_t* d_it = t_it.p;
     CK(cudaMemcpyAsync(d_in, points, (size_t) n * 12, cudaMemcpyHostToDevice, h->stream));
     const int grid = std::min<uint32_t>((n + 127) / 128, (uint32_t) h->num_sms * 8);
     {   // probes outside a remesh: masks over the last / default domain
@@ -742,7 +861,6 @@ static int eval_common(SdmHandle* h, const float* points, uint32_t n, float* out
     CK(cudaMemcpyAsync(out, d_out, (size_t) n * 4 * width, cudaMemcpyDeviceToHost, h->stream));
     if (iters) CK(cudaMemcpyAsync(iters, d_it, (size_t) n * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_in); cudaFree(d_out); if (d_it) cudaFree(d_it);
     return SDM_OK;
 }
 int sdm_eval_sdf(SdmHandle* h, const float* points, uint32_t n, float* out_sd) { return eval_common(h, points, n, out_sd, 1, 0, nullptr); }
@@ -783,9 +901,10 @@ void sdm_voxel_field_free(SdmVoxelField* field) {
 int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field) {
     if (!h || !field || (!field->voxels && field->voxel_count)) return fail(SDM_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->device));
-    uint32_t want = h->cap_vox;
-    while (want < field->voxel_count) want = grown(want);
-    int rc = ensure_capacity(h, want);
+    uint32_t want = 0;
+    int rc = capacity_for(h, field->voxel_count, &want);
+    if (rc) return rc;
+    rc = ensure_capacity(h, want);
     if (rc) return rc;
     rc = reset_state(h);
     if (rc) return rc;
@@ -798,6 +917,8 @@ int sdm_field_upload(SdmHandle* h, const SdmVoxelField* field) {
     h->cases_for_level = -1;
     h->voxel_size[0] = field->voxel_size.x; h->voxel_size[1] = field->voxel_size.y; h->voxel_size[2] = field->voxel_size.z;
     h->have_field = true; h->mesh_valid = false;
+    h->lists_level = -1;          // an uploaded list has no ancestors: cell masks
+    h->lattice.enabled = 0;       // ... and no known origin: generic vertex keys
     CK(cudaStreamSynchronize(h->stream));   // the host list may be freed by the caller right after
     return SDM_OK;
 }
@@ -809,9 +930,9 @@ int sdm_field_reset(SdmHandle* h, const SdmParams* params) {
     int rc = check_params(p);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    uint32_t want = h->cap_vox;
-    const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
-    while (want < n0) want = grown(want);
+    uint32_t want = 0;
+    rc = capacity_for(h, (uint64_t) p.init_factor * p.init_factor * p.init_factor, &want);
+    if (rc) return rc;
     rc = ensure_capacity(h, want);
     if (rc) return rc;
     rc = reset_state(h);
@@ -842,6 +963,7 @@ int sdm_field_refine(SdmHandle* h, uint32_t* out_count) {
         CK(cudaMemcpy(parents.data(), h->vox[h->cur ^ 1].p, parents.size() * 4, cudaMemcpyDeviceToHost));
         const float ps[3] = { h->voxel_size[0] * 2.0f, h->voxel_size[1] * 2.0f, h->voxel_size[2] * 2.0f };
         SdmVoxelField f { SdmPoint { ps[0], ps[1], ps[2] }, (SdmPoint*) parents.data(), n_parent };
+        if (grown(h->cap_vox) == h->cap_vox) break;
         rc = ensure_capacity(h, grown(h->cap_vox));
         if (rc) return rc;
         rc = sdm_field_upload(h, &f);
@@ -897,6 +1019,7 @@ static int run_mesh(SdmHandle* h, SdmMesh* out_mesh, bool timed) {
         std::vector<float> list((size_t) n * 3);
         if (n) CK(cudaMemcpy(list.data(), h->vox[h->cur].p, list.size() * 4, cudaMemcpyDeviceToHost));
         SdmVoxelField f { SdmPoint { h->voxel_size[0], h->voxel_size[1], h->voxel_size[2] }, (SdmPoint*) list.data(), n };
+        if (grown(h->cap_vox) == h->cap_vox) break;
         rc = ensure_capacity(h, grown(h->cap_vox));
         if (rc) return rc;
         rc = sdm_field_upload(h, &f);
@@ -929,14 +1052,14 @@ int sdm_field_triangle_soup(SdmHandle* h, SdmTriangle* out_triangles, uint32_t c
     if ((uint64_t) n * 5 > capacity) return fail(SDM_ERR_INVALID, "capacity too small");
     if (n == 0) return SDM_OK;
     CK(cudaSetDevice(h->device));
-    float* d = nullptr;
-    CK(cudaMalloc(&d, (size_t) n * 5 * sizeof(SdmTriangle)));
+    TempBuf<float> tmp;
+    CK(tmp.alloc((size_t) n * 5 * 18));
+    float* d = tmp.p;
     k_soup<<<h->g_light, 256, 0, h->stream>>>(h->state.p, h->level, h->cases.p, h->tri_off.p, h->tri_uid.p, h->upos.p, h->unrm.p, d);
     h->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_triangles, d, (size_t) n * 5 * sizeof(SdmTriangle), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d);
     return SDM_OK;
 }
 
@@ -947,9 +1070,9 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
     int rc = check_params(p);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    uint32_t want = h->cap_vox;
-    const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
-    while (want < n0) want = grown(want);
+    uint32_t want = 0;
+    rc = capacity_for(h, (uint64_t) p.init_factor * p.init_factor * p.init_factor, &want);
+    if (rc) return rc;
     static const bool trace = getenv("SDM_TRACE") != nullptr;   // developer switch: host-side phase times of sdm_remesh on stderr
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -962,12 +1085,14 @@ int sdm_remesh(SdmHandle* h, const SdmParams* params, SdmMesh* out_mesh) {
         rc = reset_state(h);
         if (rc) return rc;
         mark(h, "start");
+        NvtxRange nv(h, "sdm_remesh");
         rc = enqueue_init_field(h, p);
         if (rc) return rc;
-        for (uint32_t l = 0; l < p.levels; l++) {
-            rc = enqueue_refine(h, l + 1 == p.levels);
-            if (rc) return rc;
-        }
+        // the final voxel size is known: one inflation (slack of the mesh stage) for the list regions of all levels
+        h->delta_override = h->slack_factor * ldexpf(p.bb_size / (float) p.init_factor, -(int) p.levels);
+        for (uint32_t l = 0; l < p.levels && !rc; l++) rc = enqueue_refine(h, l + 1 == p.levels);
+        h->delta_override = 0.0f;
+        if (rc) return rc;
         rc = enqueue_mesh(h);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev1, h->stream));
@@ -1029,6 +1154,112 @@ int sdm_mesh_download_wait(SdmHandle* h) {
     return SDM_OK;
 }
 
+uint64_t sdm_hash_bytes(const void* data, size_t bytes) {
+    const unsigned char* b = (const unsigned char*) data;
+    uint64_t x = 0xcbf29ce484222325ull;
+    for (size_t i = 0; i < bytes; i++) { x ^= b[i]; x *= 0x100000001b3ull; }
+    return x;
+}
+
+// ---- OBJ writer (src/renderer/mod.rs:204 / obj crate `ObjData::save`) ---------------------------------------------------------
+namespace {
+// Rust's `{}` for f32: shortest digits that read back as the same f32 (ties: the candidate closest to the value), never
+// in exponent notation.  Digits: the correctly rounded p-digit decimal for the smallest p (1..9) that round-trips.
+int format_f32_rust(float v, char* out /* >= 64 */) {
+    if (std::isnan(v)) return snprintf(out, 64, "NaN");
+    if (std::isinf(v)) return snprintf(out, 64, v > 0 ? "inf" : "-inf");
+    if (v == 0.0f) return snprintf(out, 64, std::signbit(v) ? "-0" : "0");
+    char buf[48];
+    char digits[16] = { 0 };
+    int nd = 0, exp10 = 0;
+    const double av = std::fabs((double) v);
+    for (int p = 1; p <= 9 && nd == 0; p++) {
+        // the correctly rounded p-digit decimal and its two p-digit neighbours: at a power of two the interval of decimals that
+        // read back as v is lopsided, and the shortest representation can be a neighbour of the rounded one
+        snprintf(buf, sizeof buf, "%.*e", p - 1, av);
+        long long D = 0;
+        const char* q = buf;
+        for (; *q && *q != 'e'; q++) if (*q >= '0' && *q <= '9') D = D * 10 + (*q - '0');
+        const int e10 = atoi(q + 1);
+        double best_err = 0.0;
+        long long best = -1;
+        int best_e = 0;
+        for (int k = 0; k < 3; k++) {                                  // the rounded decimal first: it wins ties
+            const long long c = k == 0 ? D : (k == 1 ? D - 1 : D + 1);
+            if (c <= 0) continue;
+            long long cd = c;
+            int ce = e10;
+            long long lim = 1;
+            for (int i = 0; i < p; i++) lim *= 10;
+            if (cd >= lim) { cd = lim / 10; ce += 1; }                 // 999 + 1 -> 100 with the next exponent
+            else if (cd < lim / 10) { cd = lim - 1; ce -= 1; }         // 100 - 1 -> 999 with the previous exponent
+            snprintf(buf, sizeof buf, "%llde%d", cd, ce - (p - 1));
+            if (strtof(buf, nullptr) != std::fabs(v)) continue;
+            const double err = std::fabs(strtod(buf, nullptr) - av);
+            if (best < 0 || err < best_err * (1.0 - 1e-7)) { best = cd; best_err = err; best_e = ce; }
+        }
+        if (best >= 0) {
+            nd = snprintf(digits, sizeof digits, "%lld", best);
+            exp10 = best_e;
+        }
+    }
+    while (nd > 1 && digits[nd - 1] == '0') nd--;   // "1.0e0" style candidates never occur for p = shortest, but stay safe
+    char* o = out;
+    if (v < 0) *o++ = '-';
+    if (exp10 < 0) {                                // 0.000ddd
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -exp10 - 1; i++) *o++ = '0';
+        for (int i = 0; i < nd; i++) *o++ = digits[i];
+    } else if (exp10 >= nd - 1) {                   // ddd000
+        for (int i = 0; i < nd; i++) *o++ = digits[i];
+        for (int i = 0; i < exp10 - (nd - 1); i++) *o++ = '0';
+    } else {                                        // dd.ddd
+        for (int i = 0; i <= exp10; i++) *o++ = digits[i];
+        *o++ = '.';
+        for (int i = exp10 + 1; i < nd; i++) *o++ = digits[i];
+    }
+    *o = 0;
+    return (int) (o - out);
+}
+}  // namespace
+
+int sdm_mesh_save_obj(SdmHandle* h, const SdmMesh* m, const char* path) {
+    if (!m || !path) return fail(SDM_ERR_INVALID, "null argument");
+    std::vector<float> pos, nrm;
+    std::vector<uint32_t> idx;
+    const float *P = m->positions, *N = m->normals;
+    const uint32_t* I = m->indices;
+    if (m->on_device) {
+        if (!h) return fail(SDM_ERR_INVALID, "a device mesh needs its handle");
+        pos.resize((size_t) m->vertex_count * 3); nrm.resize((size_t) m->vertex_count * 3); idx.resize((size_t) m->triangle_count * 3);
+        int rc = sdm_mesh_download(h, m, pos.data(), nrm.data(), idx.data());
+        if (rc) return rc;
+        P = pos.data(); N = nrm.data(); I = idx.data();
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SDM_ERR_INVALID, std::string("cannot open ") + path);
+    std::vector<char> wb(1 << 20);
+    setvbuf(f, wb.data(), _IOFBF, wb.size());
+    char a[64], b[64], c[64];
+    for (uint32_t i = 0; i < m->vertex_count; i++) {
+        format_f32_rust(P[3 * (size_t) i], a); format_f32_rust(P[3 * (size_t) i + 1], b); format_f32_rust(P[3 * (size_t) i + 2], c);
+        fprintf(f, "v %s %s %s\n", a, b, c);
+    }
+    fputs("vt 0 0\n", f);                                    // texture: vec![[0.0, 0.0]] (src/cuda/mod.rs:306)
+    for (uint32_t i = 0; i < m->vertex_count; i++) {
+        format_f32_rust(N[3 * (size_t) i], a); format_f32_rust(N[3 * (size_t) i + 1], b); format_f32_rust(N[3 * (size_t) i + 2], c);
+        fprintf(f, "vn %s %s %s\n", a, b, c);
+    }
+    fputs("o default\ng default\n", f);                      // one object, one group, both named "default" (:308-311)
+    for (uint32_t t = 0; t < m->triangle_count; t++) {       // IndexTuple(idx, Some(0), Some(idx)) (:320), 1-based in the file
+        const uint32_t x = I[3 * (size_t) t] + 1, y = I[3 * (size_t) t + 1] + 1, z = I[3 * (size_t) t + 2] + 1;
+        fprintf(f, "f %u/1/%u %u/1/%u %u/1/%u\n", x, x, y, y, z, z);
+    }
+    const bool bad = ferror(f) != 0;
+    if (fclose(f) != 0 || bad) return fail(SDM_ERR_INVALID, std::string("write error on ") + path);
+    return SDM_OK;
+}
+
 int sdm_refine_voxel_field(SdmHandle* h, SdmVoxelField* field) {
     if (!h || !field) return fail(SDM_ERR_INVALID, "null argument");
     if (field->voxel_count == 0) return SDM_OK;   // src/cuda/mod.rs:137: size is NOT halved for an empty field
@@ -1083,9 +1314,9 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
     if (shard_count == 0 || shard_index >= shard_count) return fail(SDM_ERR_INVALID, "bad shard index / count");
     if (split_level > p.levels) split_level = p.levels;
     CK(cudaSetDevice(h->device));
-    uint32_t want = h->cap_vox;
-    const uint64_t n0 = (uint64_t) p.init_factor * p.init_factor * p.init_factor;
-    while (want < n0) want = grown(want);
+    uint32_t want = 0;
+    rc = capacity_for(h, (uint64_t) p.init_factor * p.init_factor * p.init_factor, &want);
+    if (rc) return rc;
     for (int attempt = 0; attempt < 10; attempt++) {
         rc = ensure_capacity(h, want);
         if (rc) return rc;
@@ -1096,20 +1327,22 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
         mark(h, "start");
         rc = enqueue_init_field(h, p);
         if (rc) return rc;
-        for (uint32_t l = 0; l < split_level; l++) {   // redundantly on every rank: the coarse levels are tiny
-            rc = enqueue_refine(h);
-            if (rc) return rc;
+        h->delta_override = h->slack_factor * ldexpf(p.bb_size / (float) p.init_factor, -(int) p.levels);
+        for (uint32_t l = 0; l < split_level && !rc; l++) rc = enqueue_refine(h);   // redundantly on every rank: the coarse levels are tiny
+        if (rc) { h->delta_override = 0.0f; return rc; }
+        {
+            const bool vp = h->lists_level == h->level;   // the shard's voxels keep their record indices
+            k_take_shard<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, shard_index, shard_count,
+                                                             h->shard_range.p, vp ? h->vparent[h->vp_cur].p : nullptr, vp ? h->vparent[h->vp_cur ^ 1].p : nullptr);
+            k_set_level_count<<<1, 1, 0, h->stream>>>(h->state.p, h->level, h->shard_range.p);
+            mark(h, "k_take_shard");
+            h->stats.kernel_launches += 2;
+            h->cur ^= 1;
+            if (vp) h->vp_cur ^= 1;
         }
-        k_take_shard<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, shard_index, shard_count,
-                                                         h->shard_range.p);
-        k_set_level_count<<<1, 1, 0, h->stream>>>(h->state.p, h->level, h->shard_range.p);
-        mark(h, "k_take_shard");
-        h->stats.kernel_launches += 2;
-        h->cur ^= 1;
-        for (uint32_t l = split_level; l < p.levels; l++) {
-            rc = enqueue_refine(h, l + 1 == p.levels);
-            if (rc) return rc;
-        }
+        for (uint32_t l = split_level; l < p.levels && !rc; l++) rc = enqueue_refine(h, l + 1 == p.levels);
+        h->delta_override = 0.0f;
+        if (rc) return rc;
         rc = enqueue_mesh_local(h, true);   // weld keys too: sdm_shard_local_weld follows (the root-weld fallback re-inserts)
         if (rc) return rc;
         CK(cudaEventRecord(h->ev1, h->stream));
@@ -1420,15 +1653,15 @@ int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes) {
 int sdm_selftest_math(SdmHandle* h, unsigned long long div_samples, unsigned long long* out4) {
     if (!h || !out4) return fail(SDM_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->device));
-    unsigned long long* d = nullptr;
-    CK(cudaMalloc(&d, 32));
+    TempBuf<unsigned long long> tmp;
+    CK(tmp.alloc(4));
+    unsigned long long* d = tmp.p;
     CK(dev_fill(h->stream, d, 0, 32));
     k_selftest_math<<<h->num_sms * 8, 256, 0, h->stream>>>(d, div_samples);
     h->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out4, d, 32, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d);
     return SDM_OK;
 }
 

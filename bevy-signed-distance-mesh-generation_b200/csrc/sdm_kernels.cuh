@@ -7,7 +7,7 @@
 //                     last k_refine's lattice signs cannot be reused
 //   k_tri_offsets     triangle offsets per voxel from the case table (marching_cubes.cu:24-25)
 //   k_edges           edge mid-points (marching_cubes.cu:13-16) de-duplicated by exact bit pattern in a hash table
-//   k_uid_offsets / k_assign_uids   vertex ids in list order, start points
+//                     (fast 64-bit lattice keys or generic float-bit keys); vertex ids, start points, list records
 //   k_project(+_tail) closest_surface_point per distinct mid-point (signed_distance.cu:227-240)
 //   k_build_masks(_fine)  per-cell primitive masks for large scenes (exact culling of the fold), zero-crossing flags
 //   k_vertex_normals  empirical_normal per projected vertex (signed_distance.cu:181-202) + the vertex's weld key
@@ -31,9 +31,10 @@ namespace sdm {
 
 namespace cg = cooperative_groups;
 
-enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_REFINE_EMIT = 22, TK_NORMALS = 23, TK_ORIENT = 24, TK_COUNT = 26 };
+enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_REFINE_EMIT = 22, TK_NORMALS = 23, TK_ORIENT = 24, TK_EDGES = 25, TK_COUNT = 26 };
 enum ErrFlag : uint32_t {
-    ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u
+    ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u,
+    ERR_LATTICE = 16u   // a voxel is not on the integer lattice the fast vertex keys assume: the host retries with the generic keys
 };
 
 struct DevState {
@@ -47,7 +48,8 @@ struct DevState {
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
     uint32_t cases_from_refine; // epoch of the last k_refine that met an inexact lattice (its case indices must not be used)
     uint32_t weld_dups;         // vertices whose quantised weld key was already in the table (0: the weld merges nothing)
-    unsigned long long cull_tiles, cull_prims, cull_cands, cull_fallbacks;   // k_orient's tile culling statistics
+    uint32_t n_escaped;         // vertices whose Newton iterate left the region their inherited list is proven for (general path)
+    uint32_t list_fallbacks;    // tiles of the mesh stage that had to use the cell masks instead of inherited lists
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
 };
@@ -123,7 +125,10 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 #endif
 __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __restrict__ scene, const float* __restrict__ in_vox, DevState* st, int level,
                                                 float osx, float osy, float osz, MaskGrid grid, uint32_t* __restrict__ out_m27,
-                                                uint32_t cases_epoch /* 0: no case indices wanted */, int use_cell_flags) {
+                                                uint32_t cases_epoch /* 0: no case indices wanted */, int use_cell_flags,
+                                                const uint4* __restrict__ vl_in /* records of the previous level's parents, or null */,
+                                                const uint32_t* __restrict__ vparent_in /* record index per voxel of this level */,
+                                                uint4* __restrict__ vl_out /* one record per voxel of this level, or null */, float delta) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
@@ -155,8 +160,27 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
         // none of its children survives (is_border, :36-49) - it is not evaluated and does not lengthen the tile's list.
         const bool eval = active && (!use_cell_flags || box_may_cross(grid, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz));
         const uint32_t neval = (uint32_t) __popc(__ballot_sync(0xffffffffu, eval));
-        // primitives that can matter anywhere inside this tile's parent voxels (edge = 2 * child size)
-        if (neval) tile_mask_from_box(grid, sc, eval, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
+        // Primitives that can matter anywhere inside this tile's parent voxels (edge = 2 * child size) inflated by delta: the
+        // lane's own need-list on that region is recorded (vl_out) and inherited by its children (and by the mesh stage, whose
+        // evaluation points - Newton iterates, stencil points, centroids - may leave the voxel by up to delta).  Candidates: the
+        // union of the records the lanes inherited from THEIR parents, else the cell masks.
+        if (neval && sc.wmask) {
+            const float lx = bx - delta, ly = by - delta, lz = bz - delta;
+            const float hx = bx + 2.0f * osx + delta, hy = by + 2.0f * osy + delta, hz = bz + 2.0f * osz + delta;
+            uint16_t* own = (vl_out && eval) ? reinterpret_cast<uint16_t*>(vl_out + 2 * (size_t) (p0 + lane)) : nullptr;
+            const float pad = vl_out ? 0.0021f : 0.0f;   // the mesh stage also evaluates the empirical_normal stencil (reach 2e-3)
+            uint32_t ncand = SDM_TLIST_NONE;
+            if (vl_in) {
+                uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = lo;
+                if (eval) {
+                    const uint32_t pi = vparent_in[p0 + lane];
+                    lo = __ldg(vl_in + 2 * (size_t) pi); hi = __ldg(vl_in + 2 * (size_t) pi + 1);
+                }
+                ncand = tile_union_lists(sc, lo, hi);
+            }
+            if (ncand != SDM_TLIST_NONE) tile_refine(sc, ncand, eval, lx, ly, lz, hx, hy, hz, pad, own);
+            else tile_mask_from_box(grid, sc, eval, lx, ly, lz, hx, hy, hz, own, pad);
+        }
         if (neval) work += (unsigned long long) tile_prims(sc) * 27u * neval;
         uint32_t m27 = 0;
         if (eval) {
@@ -202,7 +226,8 @@ __device__ __forceinline__ uint32_t refine_keep_mask(uint32_t m27) {
 // one parent per thread: a warp's children land in one contiguous run (4 parents per thread made the stores strided: slower)
 __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
                                                      uint32_t epoch, uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz,
-                                                     const uint32_t* __restrict__ in_m27, uint8_t* __restrict__ out_cases) {
+                                                     const uint32_t* __restrict__ in_m27, uint8_t* __restrict__ out_cases,
+                                                     uint32_t* __restrict__ vparent_out /* record index (= parent) per child, or null */) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_w[10];
     const uint32_t lane = threadIdx.x & 31u;
@@ -254,6 +279,7 @@ __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ i
                         }
                         out_cases[pos] = (uint8_t) cube;
                     }
+                    if (vparent_out) vparent_out[pos] = p;
                     pos++;
                 }
             }
@@ -373,49 +399,173 @@ __global__ void __launch_bounds__(256) k_tri_offsets(DevState* st, int level, co
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Fast vertex keys.  On a dyadic grid (the default 5 / 2^k one, any grid whose coordinates are exact multiples of half a voxel)
+// an edge mid-point is identified by three integers, its coordinates in units of half a voxel, so a table entry is ONE 64-bit
+// word (key + 1; 0 = empty) claimed with a 64-bit CAS, and entries of neighbouring mid-points are placed next to each other:
+// the 8^3 half-unit cube a key lies in selects a bucket of 64 entries (512 B), its position inside the cube the entry.
+// Voxels that are neighbours in space are neighbours in the list (children follow their parent), so a bucket is filled by one
+// thread block while it sits in L2.  (The generic table - 16-byte entries keyed by the float bits, scattered by a hash - moved
+// 1.5 GB through DRAM for 135 MB of keys: ncu, profiles/.)
+// Exactness: the kernel CHECKS, for every voxel and axis, that base, base + size and their mid-point are bit-equal to
+// o + n * half for the integers n it uses; equal keys then imply bit-equal mid-points, which is all the de-duplication needs
+// (two equal mid-points with different keys would merely be projected twice and merged by the weld, like in the reference).
+// A voxel that fails the check raises ERR_LATTICE and the host repeats the mesh stage with the generic keys.
+struct EdgeLattice { float ox, oy, oz; float hx, hy, hz; float ihx, ihy, ihz; uint32_t enabled; };
+
+__device__ __forceinline__ bool lattice_axis(float b, float s, float o, float h, float ih, int& n) {
+    n = __float2int_rn((b - o) * ih);
+    const float fn = (float) n;
+    const float hi = b + s;
+    const float mid = b * (1.0f - 0.5f) + hi * 0.5f;
+    return n >= 0 && n < (1 << 21) - 2 && __float_as_uint(o + fn * h) == __float_as_uint(b) &&
+           __float_as_uint(o + (fn + 2.0f) * h) == __float_as_uint(hi) && __float_as_uint(o + (fn + 1.0f) * h) == __float_as_uint(mid);
+}
+// lattice coordinates (half-voxel units, relative to the voxel's base index) of the mid-point of edge e
+__device__ __forceinline__ void edge_lattice_offset(int e, int& dx, int& dy, int& dz) {
+    int c0, c1;
+    mc_edge_corners(e, c0, c1);
+    const int x0 = ((c0 & 3) == 1 || (c0 & 3) == 2) ? 2 : 0, y0 = ((c0 & 3) >= 2) ? 2 : 0, z0 = (c0 >= 4) ? 2 : 0;
+    const int x1 = ((c1 & 3) == 1 || (c1 & 3) == 2) ? 2 : 0, y1 = ((c1 & 3) >= 2) ? 2 : 0, z1 = (c1 >= 4) ? 2 : 0;
+    dx = (x0 + x1) >> 1; dy = (y0 + y1) >> 1; dz = (z0 + z1) >> 1;
+}
+__device__ __forceinline__ uint32_t lattice_slot(uint32_t ux, uint32_t uy, uint32_t uz, uint32_t mask) {
+    const uint32_t h = hash96(ux >> 3, uy >> 3, uz >> 3);
+    uint32_t l = (ux & 7u) | ((uy & 7u) << 3) | ((uz & 7u) << 6);
+    l = (l * 0x9E5u) >> 5;
+    return ((h << 6) | (l & 63u)) & mask;
+}
+// find-or-insert of a 64-bit key (never 0) from `pos`; returns the entry, *won = this call created it; 0xFFFFFFFF = table full
+__device__ __forceinline__ uint32_t hash64_probe_from(unsigned long long* table, uint32_t mask, uint32_t pos, unsigned long long key, bool* won) {
+    for (uint32_t probe = 0; probe <= mask; probe++) {
+        unsigned long long cur = __ldcg(table + pos);
+        if (cur == 0ull) {
+            cur = atomicCAS(table + pos, 0ull, key);
+            if (cur == 0ull) { *won = true; return pos; }
+        }
+        if (cur == key) { *won = false; return pos; }
+        pos = (pos + 1) & mask;
+    }
+    *won = false;
+    return 0xFFFFFFFFu;
+}
+
+// Edge vertices.  One tile = 256 consecutive voxels, handed out by ticket (tiles close in the list run close in time).  Every edge
+// the case uses is looked up / claimed in the vertex table; the vertices a tile created get consecutive ids from ONE atomicAdd
+// on n_uniq per tile - ids are consecutive within a tile and tiles are nearly in list order, which is all the later per-vertex
+// kernels need (coherent neighbourhoods for their primitive lists, coalesced loads).  The id numbering is internal: output
+// order comes from the weld (first occurrence in triangle order), not from here.  For every created vertex: its start point
+// (mid-point, marching_cubes.cu:13-16), its list record (the creating voxel's parent) and the id in the entry's side array.
+template <bool LATTICE>
 __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
-                                               const uint32_t* __restrict__ tri_off, uint4* table, uint32_t table_mask,
-                                               uint32_t* __restrict__ slot_ref, uint16_t* __restrict__ won, float sx, float sy, float sz) {
+                                               const uint32_t* __restrict__ tri_off, void* table_raw, uint32_t table_mask,
+                                               uint32_t* __restrict__ slot_ref, uint32_t* __restrict__ tri_rec, const uint32_t* __restrict__ vparent,
+                                               uint32_t* __restrict__ entry_uid, float* __restrict__ ustart, uint32_t* __restrict__ urec,
+                                               EdgeLattice lat, float sx, float sy, float sz, uint32_t cap_uniq) {
     __shared__ McShared mc;
     __shared__ uint32_t s_eref[12 * 256];   // [edge][thread]: bank-conflict-free dynamic indexing by edge
+    __shared__ uint32_t s_w[9];
+    __shared__ uint32_t s_tile, s_base;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         mc.packed[i] = c_mc_packed[i]; mc.edgemask[i] = c_mc_edgemask[i]; mc.ntri[i] = c_mc_ntri[i];
     }
     __syncthreads();
     if (st->error_flags) return;
     const uint32_t n = st->level_count[level];
-    bool full = false;
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
-        const uint32_t cube_index = cases[v];
-        const uint32_t emask = mc.edgemask[cube_index];
+    const uint32_t ntiles = (n + 255u) >> 8;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint4* table16 = reinterpret_cast<uint4*>(table_raw);
+    unsigned long long* table8 = reinterpret_cast<unsigned long long*>(table_raw);
+    bool full = false, off_lattice = false;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_EDGES], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const uint32_t v = (tile << 8) + threadIdx.x;
+        const uint32_t cube_index = v < n ? cases[v] : 0u;
+        const uint32_t emask = mc.edgemask[cube_index];   // case 0 uses no edge
         uint32_t won_mask = 0;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        int nx = 0, ny = 0, nz = 0;
         if (emask) {
-            const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
-            // Both passes walk the set bits of the case's edge mask (4 edges on average; unrolled over all 12, the warp ran
-            // every edge's code because some lane always uses it).
-            // pass 1: start the table lines of all used edges on their way to L2 (the probes below are dependent chains)
+            bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2];
+            if (LATTICE) {
+                const bool ok = lattice_axis(bx, sx, lat.ox, lat.hx, lat.ihx, nx) & lattice_axis(by, sy, lat.oy, lat.hy, lat.ihy, ny) &
+                                lattice_axis(bz, sz, lat.oz, lat.hz, lat.ihz, nz);
+                if (!ok) { off_lattice = true; nx = ny = nz = 0; }
+            }
+            // Both passes walk the set bits of the case's edge mask (4 edges on average).
+            // pass 1: start the table lines of all used edges on their way (the probes below are dependent chains)
             for (uint32_t m = emask; m; m &= m - 1u) {
                 const int e = __ffs((int) m) - 1;
-                float mx, my, mz;
-                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                uint32_t kx = __float_as_uint(mx);
-                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
-                const uint32_t pos0 = hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask;
-                prefetch_l2(table + pos0);
+                uint32_t pos0;
+                if (LATTICE) {
+                    int dx, dy, dz;
+                    edge_lattice_offset(e, dx, dy, dz);
+                    pos0 = lattice_slot((uint32_t) (nx + dx), (uint32_t) (ny + dy), (uint32_t) (nz + dz), table_mask);
+                    prefetch_l2(table8 + pos0);
+                } else {
+                    float mx, my, mz;
+                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                    uint32_t kx = __float_as_uint(mx);
+                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
+                    pos0 = hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask;
+                    prefetch_l2(table16 + pos0);
+                }
                 s_eref[e * 256 + threadIdx.x] = pos0;
             }
             // pass 2: find-or-insert from the stored start position; remember the entry per edge and which ones this voxel created
             for (uint32_t m = emask; m; m &= m - 1u) {
                 const int e = __ffs((int) m) - 1;
-                float mx, my, mz;
-                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                uint32_t kx = __float_as_uint(mx);
-                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
                 bool w;
-                const uint32_t pos = hash_probe_from(table, table_mask, s_eref[e * 256 + threadIdx.x], kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
-                if (pos == 0xFFFFFFFFu) full = true;
+                uint32_t pos;
+                if (LATTICE) {
+                    int dx, dy, dz;
+                    edge_lattice_offset(e, dx, dy, dz);
+                    const unsigned long long key = 1ull + ((unsigned long long) (uint32_t) (nx + dx) | ((unsigned long long) (uint32_t) (ny + dy) << 21) |
+                                                           ((unsigned long long) (uint32_t) (nz + dz) << 42));
+                    pos = hash64_probe_from(table8, table_mask, s_eref[e * 256 + threadIdx.x], key, &w);
+                } else {
+                    float mx, my, mz;
+                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                    uint32_t kx = __float_as_uint(mx);
+                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
+                    pos = hash_probe_from(table16, table_mask, s_eref[e * 256 + threadIdx.x], kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
+                }
+                if (pos == 0xFFFFFFFFu) { full = true; w = false; }
                 if (w) won_mask |= 1u << e;
                 s_eref[e * 256 + threadIdx.x] = pos;
+            }
+        }
+        // ids of the vertices this tile created: block scan of the counts + one atomicAdd
+        const uint32_t cnt = __popc(won_mask);
+        const uint32_t incl = warp_inclusive_sum(cnt, lane);
+        if (lane == 31u) s_w[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (uint32_t w = 0; w < 8u; w++) { const uint32_t t = s_w[w]; s_w[w] = run; run += t; }
+            s_w[8] = run;
+            s_base = run ? atomicAdd(&st->n_uniq, run) : 0u;
+        }
+        __syncthreads();
+        const uint32_t total = s_w[8], base = s_base;
+        if (base + total > cap_uniq || base + total < base) {
+            if (threadIdx.x == 0) atomicOr(&st->error_flags, ERR_UNIQ_CAP);
+            continue;
+        }
+        if (emask) {
+            const uint32_t rec = vparent ? vparent[v] : 0u;
+            uint32_t uid = base + s_w[warp] + incl - cnt;
+            for (uint32_t m = won_mask; m; m &= m - 1u) {
+                const int e = __ffs((int) m) - 1;
+                float mx, my, mz;
+                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
+                urec[uid] = rec;
+                entry_uid[s_eref[e * 256 + threadIdx.x]] = uid;   // 4-byte side array of the table; readers come after the kernel boundary
+                uid++;
             }
             const uint32_t ntri = mc.ntri[cube_index];
             const uint32_t t0 = tri_off[v];
@@ -424,92 +574,11 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
                 const uint32_t e = (uint32_t) ((packed >> (4 * j)) & 0xFull);
                 slot_ref[3 * (size_t) t0 + j] = s_eref[e * 256 + threadIdx.x];
             }
+            for (uint32_t j = 0; j < ntri; j++) tri_rec[t0 + j] = rec;
         }
-        won[v] = (uint16_t) won_mask;
     }
     if (full) atomicOr(&st->error_flags, ERR_HASH_FULL);
-}
-
-// uid_base[v] = number of vertices created by the voxels before v (list order); same streaming scan as k_tri_offsets
-__global__ void __launch_bounds__(256) k_uid_offsets(DevState* st, int level, const uint16_t* __restrict__ won, uint32_t* __restrict__ uid_base,
-                                                     uint32_t epoch, uint64_t* tiles, uint32_t cap_uniq) {
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_w[10];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = st->level_count[level];
-    const uint32_t per_tile = blockDim.x * 4u;
-    const uint32_t ntiles = (n + per_tile - 1u) / per_tile;
-    const bool bad = st->error_flags != 0u;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_ASSIGN], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= ntiles || bad) {
-            if ((tile == 0 || bad) && threadIdx.x == 0) st->n_uniq = 0;
-            break;
-        }
-        const uint32_t v0 = tile * per_tile + threadIdx.x * 4u;
-        uint32_t c[4] = { 0, 0, 0, 0 };
-        if (v0 + 3u < n) {
-            const ushort4 q = *reinterpret_cast<const ushort4*>(won + v0);
-            c[0] = __popc(q.x); c[1] = __popc(q.y); c[2] = __popc(q.z); c[3] = __popc(q.w);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (v0 + j < n) c[j] = __popc(won[v0 + j]);
-        }
-        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
-        const uint32_t incl = warp_inclusive_sum(mine, lane);
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t end;
-        const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, end);
-        uint32_t o = base + incl - mine;
-        if (v0 + 3u < n) {
-            *reinterpret_cast<uint4*>(uid_base + v0) = make_uint4(o, o + c[0], o + c[0] + c[1], o + c[0] + c[1] + c[2]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) { if (v0 + j < n) uid_base[v0 + j] = o; o += c[j]; }
-        }
-        if (tile == ntiles - 1 && threadIdx.x == 0) {
-            if (end > cap_uniq) atomicOr(&st->error_flags, ERR_UNIQ_CAP);
-            st->n_uniq = min(end, cap_uniq);
-        }
-    }
-}
-
-// start points and ids of the vertices each voxel created (no ordering between voxels any more: plain grid-stride loop)
-__global__ void __launch_bounds__(256) k_assign_uids(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
-                                                     const uint32_t* __restrict__ tri_off, const uint16_t* __restrict__ won,
-                                                     const uint32_t* __restrict__ uid_base, uint32_t* __restrict__ entry_uid,
-                                                     const uint32_t* __restrict__ slot_ref, float* __restrict__ ustart, float sx, float sy, float sz) {
-    __shared__ unsigned long long s_packed[256];
-    __shared__ unsigned char s_ntri[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_packed[i] = c_mc_packed[i]; s_ntri[i] = c_mc_ntri[i]; }
-    __syncthreads();
-    if (st->error_flags) return;
-    const uint32_t n = st->level_count[level];
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
-        uint32_t m = won[v];
-        if (!m) continue;
-        const float bx = vox[3 * (size_t) v], by = vox[3 * (size_t) v + 1], bz = vox[3 * (size_t) v + 2];
-        const uint32_t cube_index = cases[v];
-        const unsigned long long packed = s_packed[cube_index];
-        const uint32_t nslots = 3u * s_ntri[cube_index];
-        const uint32_t t0 = tri_off[v];
-        uint32_t uid = uid_base[v];
-        while (m) {
-            const int e = __ffs((int) m) - 1;
-            m &= m - 1u;
-            float mx, my, mz;
-            edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-            ustart[3 * (size_t) uid] = mx; ustart[3 * (size_t) uid + 1] = my; ustart[3 * (size_t) uid + 2] = mz;
-            uint32_t j = 0;
-            while (j < nslots && (uint32_t) ((packed >> (4 * j)) & 0xFull) != (uint32_t) e) j++;   // an edge of the case's mask is used by a triangle
-            // vertex id of the table entry: a 4-byte side array (it stays in L2, the 16-byte entries do not)
-            if (j < nslots) entry_uid[slot_ref[3 * (size_t) t0 + j]] = uid;   // readers come after the kernel boundary
-            uid++;
-        }
-    }
+    if (off_lattice) atomicOr(&st->error_flags, ERR_LATTICE);
 }
 
 // the mesh stage may be re-run on the same field: reset its counters and tickets (not error_flags, not the refine state)
@@ -519,7 +588,7 @@ __global__ void k_reset_mesh_state(DevState* st) {
     for (int i = TK_CLASSIFY; i < TK_COUNT; i++) st->ticket[i] = 0;
     st->n_stragglers = 0; st->weld_dups = 0;
     st->newton_iters = 0;
-    st->cull_tiles = 0; st->cull_prims = 0; st->cull_cands = 0; st->cull_fallbacks = 0;
+    st->n_escaped = 0; st->list_fallbacks = 0;
     for (int i = WK_CLASSIFY; i < 6; i++) st->prim_evals[i] = 0;   // refine's counter is reset with the field
 }
 
@@ -531,11 +600,14 @@ __device__ __forceinline__ uint32_t weld_table_size(uint32_t n_uniq, uint32_t ma
     return s;
 }
 __global__ void __launch_bounds__(256) k_clear_weld_state(DevState* st, uint32_t* __restrict__ first_slot, uint32_t* __restrict__ first_bits,
-                                                          uint4* __restrict__ table2, uint32_t max_entries, uint32_t cap_uniq, int clear_first_slot) {
+                                                          uint4* __restrict__ table2, uint32_t max_entries, uint32_t cap_uniq, int clear_first_slot,
+                                                          uint32_t* __restrict__ uesc) {
     const uint32_t nu = min(st->n_uniq, cap_uniq), T = st->n_tris_raw;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     if (clear_first_slot)
         for (uint32_t i = tid; i < nu; i += stride) first_slot[i] = 0xFFFFFFFFu;
+    if (uesc)
+        for (uint32_t i = tid; i < (nu + 31u) / 32u; i += stride) uesc[i] = 0u;
     const uint32_t nw = (3u * T + 31u) / 32u + 1u;
     for (uint32_t i = tid; i < nw; i += stride) first_bits[i] = 0u;
     const uint32_t ts = weld_table_size(nu, max_entries);
@@ -559,13 +631,18 @@ struct Straggler { uint32_t uid, it; float g[3]; float s[3]; uint32_t power, lam
 #endif
 __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart,
                                                  float* __restrict__ upos, uint32_t cap_uniq, Straggler* __restrict__ stragglers,
-                                                 uint32_t cap_stragglers, MaskGrid grid, uint32_t max_chunk) {
+                                                 uint32_t cap_stragglers, MaskGrid grid, uint32_t max_chunk,
+                                                 const uint4* __restrict__ vl /* list records, or null: cell masks only */,
+                                                 const uint32_t* __restrict__ urec, uint32_t* __restrict__ uesc, float slack2) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = min(st->n_uniq, cap_uniq);
     if (st->error_flags) return;
+    const bool lists = vl != nullptr && sc.wmask != nullptr;
     bool have = false;
+    bool inr = true;   // the lane's iterate is inside the region its vertex's list record is proven for
+    uint32_t rec = 0, fallbacks = 0;
     uint32_t uid = 0, it = 0, iters_done = 0;
     unsigned long long work = 0;
     float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -596,6 +673,8 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
                 uid = idx; it = 0; have = true;
                 gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
                 cyc.start(gx, gy, gz);
+                inr = true;
+                if (lists) rec = urec[idx];
             }
             chunk_next = min(chunk_next + (uint32_t) __popc(need), chunk_end);
         }
@@ -603,17 +682,27 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
             if (drained || chunk_next >= chunk_end) { if (drained) break; }
             continue;   // fetch the next chunk
         }
-        tile_mask_from_point(grid, sc, have, gx, gy, gz);   // cells of the lanes' current iterates
+        // The tile's primitive list: the union of the lanes' inherited records (valid while every iterate stays within `slack` of
+        // its start point, which lies on the creating voxel: k_refine proved the records on the voxels inflated by that much),
+        // else the cell masks at the lanes' current iterates.
+        bool listed = false;
+        if (lists && __all_sync(0xffffffffu, !have || inr)) listed = tile_list_from_records(sc, have, vl, rec);
+        if (!listed) { tile_mask_from_point(grid, sc, have, gx, gy, gz); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, have));
         if (have) {
             const bool collision = newton_step(sc, gx, gy, gz);
             it++;
             if (!collision) cyc.observe(gx, gy, gz, it);
+            if (lists) {
+                const float ex = gx - ustart[3 * (size_t) uid], ey = gy - ustart[3 * (size_t) uid + 1], ez = gz - ustart[3 * (size_t) uid + 2];
+                inr = ex * ex + ey * ey + ez * ez <= slack2;   // NaN: outside
+            }
             if (collision || it >= cyc.stop_at) {   // for (i = 0; !collision && i < 10000; i++)
                 upos[3 * (size_t) uid] = gx; upos[3 * (size_t) uid + 1] = gy; upos[3 * (size_t) uid + 2] = gz;
+                if (lists && !inr) { atomicOr(uesc + (uid >> 5), 1u << (uid & 31u)); atomicAdd(&st->n_escaped, 1u); }
                 iters_done += it;
                 have = false;
-            } else if (it >= SDM_NEWTON_BULK_ITERS) {
+            } else if (it >= SDM_NEWTON_BULK_ITERS || !inr) {   // slow, or left its list's region: the tail kernel takes over (cell masks)
                 const uint32_t slot = atomicAdd(&st->n_stragglers, 1u);
                 if (slot < cap_stragglers) {
                     Straggler r;
@@ -633,6 +722,7 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
     for (int o = 16; o > 0; o >>= 1) iters_done += __shfl_xor_sync(0xffffffffu, iters_done, o);
     if (lane == 0 && iters_done) atomicAdd(&st->newton_iters, (unsigned long long) iters_done);
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_PROJECT], work);
+    if (lane == 0 && fallbacks) atomicAdd(&st->list_fallbacks, fallbacks);
 }
 
 // Tail phase: one HALF-WARP per straggler.  The 13 evaluation points of a Newton step (the iterate and the 12 stencil
@@ -640,7 +730,8 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
 // thirteen; every lane then forms the same update from the 13 shuffled values (identical arithmetic => identical bits).
 // Two vertices per warp keep 26 of 32 lanes busy when there are many stragglers (Mandelbulb: ~1 % of all vertices).
 __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ scene, DevState* st, float* __restrict__ upos,
-                                                      const Straggler* __restrict__ stragglers, uint32_t cap_stragglers, MaskGrid grid) {
+                                                      const Straggler* __restrict__ stragglers, uint32_t cap_stragglers, MaskGrid grid,
+                                                      const float* __restrict__ ustart, uint32_t* __restrict__ uesc /* null: no list records in use */, float slack2) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
@@ -705,6 +796,10 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
         if (idx < n && hl == 0) {
             upos[3 * (size_t) r.uid] = gx; upos[3 * (size_t) r.uid + 1] = gy; upos[3 * (size_t) r.uid + 2] = gz;
             extra_iters += it - r.it;
+            if (uesc) {   // the later per-vertex / per-triangle kernels must not use this vertex's list record if it ended outside its region
+                const float ex = gx - ustart[3 * (size_t) r.uid], ey = gy - ustart[3 * (size_t) r.uid + 1], ez = gz - ustart[3 * (size_t) r.uid + 2];
+                if (!(ex * ex + ey * ey + ez * ez <= slack2)) { atomicOr(uesc + (r.uid >> 5), 1u << (r.uid & 31u)); atomicAdd(&st->n_escaped, 1u); }
+            }
         }
     }
     extra_iters += __shfl_xor_sync(0xffffffffu, extra_iters, 16);
@@ -734,11 +829,14 @@ __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* _
 #endif
 __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
                                                         float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
-                                                        uint32_t weld_max_entries, uint32_t* __restrict__ wref) {
+                                                        uint32_t weld_max_entries, uint32_t* __restrict__ wref,
+                                                        const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, const uint32_t* __restrict__ uesc) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t n = min(st->n_uniq, cap_uniq);
     if (st->error_flags) return;
+    const bool lists = vl != nullptr && sc.wmask != nullptr;
+    uint32_t fallbacks = 0;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -760,7 +858,12 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
         if (weld_table && active) wref[u] = weld_insert_key(st, upos, u, weld_table, table_mask);
-        tile_mask_from_point(grid, sc, active, x, y, z);
+        bool listed = false;
+        if (lists) {
+            const bool esc = active && ((uesc[u >> 5] >> (u & 31u)) & 1u);
+            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, active, vl, active ? urec[u] : 0u);
+        }
+        if (!listed) { tile_mask_from_point(grid, sc, active, x, y, z); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 12u * min(32u, n - u0);
         if (active) {
             float nx, ny, nz;
@@ -769,17 +872,21 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
         }
     }
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_NORMALS], work);
+    if (lane == 0 && fallbacks) atomicAdd(&st->list_fallbacks, fallbacks);
 }
 
 // Per raw triangle: orientation test and the reference host's triangle filter.
 __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __restrict__ scene, DevState* st, const uint32_t* __restrict__ entry_uid,
                                                 const uint32_t* __restrict__ slot_ref, const float* __restrict__ upos,
                                                 uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
-                                                uint32_t* __restrict__ tri_valid_bits, MaskGrid grid) {
+                                                uint32_t* __restrict__ tri_valid_bits, MaskGrid grid,
+                                                const uint4* __restrict__ vl, const uint32_t* __restrict__ tri_rec, const uint32_t* __restrict__ uesc) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t T = st->n_tris_raw;
     if (st->error_flags) return;
+    const bool lists = vl != nullptr && sc.wmask != nullptr;
+    uint32_t fallbacks = 0;
     const uint32_t lane = threadIdx.x & 31u;
     // warp-contiguous mapping so that one lane can write the 32 validity bits of a warp's triangles
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -808,7 +915,15 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
             // (v0 + v1 + v2) / 3.0f   (compute_mesh_generation.cu:104)
             mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f; my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f; mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
         }
-        tile_mask_from_point(grid, sc, t < T, mx, my, mz);
+        // The centroid lies in the convex hull of the three vertices; each ended within `slack` of its start point on this
+        // triangle's voxel (unless flagged), so the centroid is inside the region the voxel's list record is proven for.
+        bool listed = false;
+        if (lists) {
+            bool esc = false;
+            if (t < T) esc = (((uesc[u[0] >> 5] >> (u[0] & 31u)) | (uesc[u[1] >> 5] >> (u[1] & 31u)) | (uesc[u[2] >> 5] >> (u[2] & 31u))) & 1u) != 0u;
+            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, t < T, vl, t < T ? tri_rec[t] : 0u);
+        }
+        if (!listed) { tile_mask_from_point(grid, sc, t < T, mx, my, mz); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 12u * min(32u, T - t0);
         if (t < T) {
             // normalize(cross(v1 - v0, v2 - v0))   (:103)
@@ -835,6 +950,7 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
         if (lane == 0) tri_valid_bits[t0 >> 5] = bits;
     }
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_ORIENT], work);
+    if (lane == 0 && fallbacks) atomicAdd(&st->list_fallbacks, fallbacks);
 }
 
 // The reference-order weld (src/cuda/mod.rs:263-296).  A vertex's key entry is created by weld_insert_key (fused into
@@ -994,10 +1110,13 @@ __global__ void __launch_bounds__(256) k_soup(DevState* st, int level, const uin
 // copied to the front of the other ping-pong buffer.  Children keep their parent's order (compute_mesh_generation.cu:51)
 // and level 0 is x-major (src/cuda/mod.rs:110-119), so a contiguous part of the list is an x-slab at every level.
 __global__ void __launch_bounds__(256) k_take_shard(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
-                                                    uint32_t shard, uint32_t count, uint32_t* __restrict__ range_out) {
+                                                    uint32_t shard, uint32_t count, uint32_t* __restrict__ range_out,
+                                                    const uint32_t* __restrict__ vp_in, uint32_t* __restrict__ vp_out) {
     const uint32_t n = st->level_count[level];
     const uint32_t lo = (uint32_t) ((uint64_t) n * shard / count), hi = (uint32_t) ((uint64_t) n * (shard + 1) / count);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * (hi - lo); i += gridDim.x * blockDim.x) out_vox[i] = in_vox[3 * (size_t) lo + i];
+    if (vp_in)   // list record (= parent) indices travel with the voxels
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < hi - lo; i += gridDim.x * blockDim.x) vp_out[i] = vp_in[lo + i];
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) { range_out[0] = lo; range_out[1] = hi; range_out[2] = n; }
 }
@@ -1291,7 +1410,7 @@ __global__ void __launch_bounds__(256) k_build_masks(const uint4* __restrict__ s
     // conflict, and staging 64 KB per block would cap occupancy)
     const SceneHeader hdr = *reinterpret_cast<const SceneHeader*>(scene);
     SceneView sc;
-    sc.runs = nullptr; sc.nruns = 0; sc.nprims = hdr.nprims; sc.wmask = nullptr; sc.W = 0; sc.tcand = nullptr; sc.tlist = nullptr; sc.tcount = nullptr;
+    sc.runs = nullptr; sc.nruns = 0; sc.nprims = hdr.nprims; sc.wmask = nullptr; sc.W = 0; sc.tlist = nullptr; sc.tcount = nullptr;
     sc.prims = reinterpret_cast<const DevPrim*>(scene + 1 + hdr.nruns);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -58,7 +58,8 @@ class _Stats(ctypes.Structure):
     _fields_ = [
         ("kernel_launches", ctypes.c_uint64), ("sdf_evals", ctypes.c_uint64), ("level_counts", ctypes.c_uint32 * 16),
         ("unique_vertices", ctypes.c_uint32), ("raw_triangles", ctypes.c_uint32), ("last_gpu_ms", ctypes.c_float),
-        ("reserved", ctypes.c_uint32), ("prim_evals", ctypes.c_uint64 * 6),
+        ("escaped_vertices", ctypes.c_uint32), ("prim_evals", ctypes.c_uint64 * 6),
+        ("list_fallback_tiles", ctypes.c_uint32), ("stragglers", ctypes.c_uint32), ("newton_iterations", ctypes.c_uint64),
     ]
 
 
@@ -88,6 +89,7 @@ ABI_SYMBOLS = [
     "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
     "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_fixup",
     "sdm_shard_welded_buffers", "sdm_shard_reserve_welded",
+    "sdm_mesh_save_obj", "sdm_hash_bytes",
     "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
 
@@ -114,6 +116,8 @@ def load_library() -> ctypes.CDLL:
         lib.sdm_destroy.restype = None
         lib.sdm_voxel_field_free.restype = None
         lib.sdm_mesh_free.restype = None
+        lib.sdm_hash_bytes.restype = ctypes.c_uint64
+        lib.sdm_hash_bytes.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         _lib = lib
     return _lib
 
@@ -143,23 +147,18 @@ class Mesh:
         return int(self.positions.shape[0])
 
     def save_obj(self, path) -> None:
-        """Writes the mesh the way the reference does when the `Mesh` stage is advanced (src/renderer/mod.rs:204,
-        `obj.save("generated_mesh.obj")` on the ObjData built at src/cuda/mod.rs:303-326): all `v` lines, the single
-        `vt 0 0`, all `vn` lines, object and group "default", and one `f a/1/a b/1/b c/1/c` per triangle (1-based;
-        position index == normal index, texture index 0 -> 1).  Floats use Rust's `{}` formatting of f32: shortest
-        digits that round-trip, positional notation.  (The `obj` crate 0.10.2 is not vendored in the reference tree,
-        so the line layout is restated from its documented format - unpinned.)"""
-        f32 = lambda x: np.format_float_positional(np.float32(x), unique=True, trim="-") if np.isfinite(x) else ("NaN" if np.isnan(x) else ("inf" if x > 0 else "-inf"))
-        with open(path, "w") as out:
-            for p in self.positions:
-                out.write(f"v {f32(p[0])} {f32(p[1])} {f32(p[2])}\n")
-            out.write("vt 0 0\n")
-            for n in self.normals:
-                out.write(f"vn {f32(n[0])} {f32(n[1])} {f32(n[2])}\n")
-            out.write("o default\ng default\n")
-            for t in self.indices:
-                a, b, c = int(t[0]) + 1, int(t[1]) + 1, int(t[2]) + 1
-                out.write(f"f {a}/1/{a} {b}/1/{b} {c}/1/{c}\n")
+        """`obj.save("generated_mesh.obj")` of the reference's `Mesh` stage (src/renderer/mod.rs:204) through the C ABI's
+        sdm_mesh_save_obj (include/sdfmesh.h has the format; the `obj` crate 0.10.2 is not vendored in the reference tree, so
+        the line layout is restated from its documented writer - unpinned)."""
+        lib = load_library()
+        pos = np.ascontiguousarray(self.positions, np.float32)
+        nrm = np.ascontiguousarray(self.normals, np.float32)
+        idx = np.ascontiguousarray(self.indices, np.uint32)
+        m = _Mesh(pos.ctypes.data_as(ctypes.c_void_p), nrm.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p),
+                  ctypes.c_uint32(pos.shape[0]), ctypes.c_uint32(idx.shape[0]), ctypes.c_int32(0), ctypes.c_int32(0))
+        rc = lib.sdm_mesh_save_obj(None, ctypes.byref(m), str(path).encode())
+        if rc:
+            raise SdfMeshError(rc, lib.sdm_last_error().decode())
 
     def bevy_attributes(self) -> dict:
         """The three buffers `obj_to_bevy_mesh` hands to Bevy (src/renderer/mod.rs:110-128): ATTRIBUTE_POSITION and
@@ -400,6 +399,10 @@ class CudaHandler:
     def shard_reserve_welded(self, total_vertices: int, total_triangles: int) -> None:
         self._check(self._lib.sdm_shard_reserve_welded(self._h, ctypes.c_uint32(total_vertices), ctypes.c_uint32(total_triangles)))
 
+    def save_obj(self, m, path) -> None:
+        """sdm_mesh_save_obj of a device-resident mesh (`remesh(..., download=False)`)."""
+        self._check(self._lib.sdm_mesh_save_obj(self._h, ctypes.byref(m), str(path).encode()))
+
     def download_into(self, m, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:
         """sdm_mesh_download into caller-provided (e.g. pinned) host memory."""
         self._check(self._lib.sdm_mesh_download(self._h, ctypes.byref(m), ctypes.c_void_p(positions_ptr), ctypes.c_void_p(normals_ptr),
@@ -438,4 +441,6 @@ class CudaHandler:
         self._check(self._lib.sdm_get_stats(self._h, ctypes.byref(s)))
         return dict(kernel_launches=int(s.kernel_launches), sdf_evals=int(s.sdf_evals), level_counts=list(s.level_counts),
                     unique_vertices=int(s.unique_vertices), raw_triangles=int(s.raw_triangles), last_gpu_ms=float(s.last_gpu_ms),
+                    escaped_vertices=int(s.escaped_vertices), list_fallback_tiles=int(s.list_fallback_tiles), stragglers=int(s.stragglers),
+                    newton_iterations=int(s.newton_iterations),
                     prim_evals=dict(zip(("refine", "classify", "project", "tail", "normals", "orient"), [int(x) for x in s.prim_evals])))

@@ -157,6 +157,16 @@ int sdm_mesh_download(SdmHandle* h, const SdmMesh* device_mesh, float* positions
  * should be pinned.  sdm_mesh_download_wait blocks until all issued downloads have landed. */
 int sdm_mesh_download_async(SdmHandle* h, const SdmMesh* device_mesh, float* positions, float* normals, uint32_t* indices);
 int sdm_mesh_download_wait(SdmHandle* h);
+/* Consumer hand-off, file form: writes the mesh the way the reference does when its `Mesh` stage is advanced
+ * (src/renderer/mod.rs:204 `obj.save("generated_mesh.obj")` on the ObjData built at src/cuda/mod.rs:303-326, obj crate 0.10.2):
+ * all `v x y z` lines, the single `vt 0 0`, all `vn x y z` lines, `o default`, `g default`, then one
+ * `f a/1/a b/1/b c/1/c` per triangle (1-based; position index == normal index, texture index 0 -> 1).  Numbers are written
+ * as Rust's `{}` writes an f32: the shortest decimal digits that round-trip, positional notation, `NaN` / `inf` / `-inf`.
+ * `mesh` may be a device mesh of this handle (it is downloaded first) or a host mesh (h may then be NULL).  An empty mesh
+ * gives the header lines only (src/cuda/mod.rs:327-345). */
+int sdm_mesh_save_obj(SdmHandle* h, const SdmMesh* mesh, const char* path);
+/* FNV-1a-64 over raw bytes (the checksum of tests/golden and of bench.py's `mesh_fnv`). */
+uint64_t sdm_hash_bytes(const void* data, size_t bytes);
 /* The reference's raw output format: 5 Triangle slots per voxel, NaN-padded
  * (compute_mesh_generation.cu:64-120), to host (capacity in triangles, >= 5 * voxel_count). */
 int sdm_field_triangle_soup(SdmHandle* h, SdmTriangle* out_triangles, uint32_t capacity);
@@ -238,9 +248,12 @@ typedef struct SdmStats {
     uint32_t unique_vertices;      /* distinct edge midpoints projected in the last mesh */
     uint32_t raw_triangles;        /* triangles before the finite-vertex filter */
     float last_gpu_ms;             /* CUDA-event time of the last remesh / mesh call on the handle's stream */
-    uint32_t reserved;
+    uint32_t escaped_vertices;     /* vertices whose Newton iterate left the region of their inherited primitive list (general path) */
     uint64_t prim_evals[6];        /* (primitive, point) distance evaluations actually folded by the last remesh, per stage:
                                       refine, classify, project, project tail, vertex normals, orient (after culling) */
+    uint32_t list_fallback_tiles;  /* warp tiles of the mesh stage that used the cell masks although list records existed */
+    uint32_t stragglers;           /* vertices handed to the Newton tail kernel (>= 40 iterations, or escaped) */
+    uint64_t newton_iterations;    /* closest_surface_point iterations of the last mesh (after exact cycle short-cuts) */
 } SdmStats;
 int sdm_get_stats(SdmHandle* h, SdmStats* out);
 /* Per-kernel timing for the bench's roofline line: when enabled, sdm_remesh records a CUDA event on the handle's

@@ -187,6 +187,39 @@ class RefHost:
         self.lib.ref_mesh(_fp(vox), ctypes.c_uint32(vox.shape[0]), _fp(vs), _fp(tris))
         return tris
 
+    # ---- functor templates over the reference's own functions (ref_functor.inc): scene 1 = sd_obj, 2 = sd_unit_mandelbulb,
+    #      3 = SdmPrimitive table fold (un-culled) --------------------------------------------------------------------------
+    def set_threads(self, n: int) -> None:
+        self.lib.ref_set_num_threads(int(n))
+
+    def threads(self) -> int:
+        return int(self.lib.ref_num_threads())
+
+    def tpl_refine_raw(self, scene_id, table, vox, vs):
+        vox = np.ascontiguousarray(vox, np.float32).reshape(-1, 3)
+        vs = np.ascontiguousarray(vs, np.float32)
+        table = np.ascontiguousarray(table) if table is not None else np.zeros(0, np.uint8)
+        out = np.empty((vox.shape[0] * 8, 3), np.float32)
+        self.lib.ref_tpl_refine(ctypes.c_int(scene_id), table.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(table.shape[0]), _fp(vox),
+                                ctypes.c_uint32(vox.shape[0]), _fp(vs), _fp(out))
+        return out
+
+    def tpl_mesh_raw(self, scene_id, table, vox, vs):
+        vox = np.ascontiguousarray(vox, np.float32).reshape(-1, 3)
+        vs = np.ascontiguousarray(vs, np.float32)
+        table = np.ascontiguousarray(table) if table is not None else np.zeros(0, np.uint8)
+        tris = np.empty((vox.shape[0] * 5, 18), np.float32)
+        self.lib.ref_tpl_mesh(ctypes.c_int(scene_id), table.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(table.shape[0]), _fp(vox),
+                              ctypes.c_uint32(vox.shape[0]), _fp(vs), _fp(tris))
+        return tris
+
+    def tpl_sdf(self, table, pts):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        table = np.ascontiguousarray(table)
+        out = np.empty(pts.shape[0], np.float32)
+        self.lib.ref_tpl_sdf(table.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(table.shape[0]), _fp(pts), ctypes.c_uint32(pts.shape[0]), _fp(out))
+        return out
+
     def _pts(self, fn, pts, width):
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
         out = np.empty((pts.shape[0], width) if width > 1 else pts.shape[0], np.float32)
@@ -244,7 +277,8 @@ class RefHost:
 
 class RefGpu:
     """The reference's kernels compiled by nvcc for sm_100a with IEEE flags (oracle/_ref/libref_gpu.so).
-    scene: 0 = unmodified reference kernels (sd_obj), 1 = functor templates with sd_obj, 2 = with sd_unit_mandelbulb."""
+    scene: 0 = unmodified reference kernels (sd_obj), 1 = functor templates with sd_obj, 2 = with sd_unit_mandelbulb,
+    3 = with the SdmPrimitive table fold of set_table() (reference primitives, un-culled)."""
 
     def __init__(self):
         path = HERE / "_ref" / "libref_gpu.so"
@@ -255,6 +289,11 @@ class RefGpu:
     @staticmethod
     def available() -> bool:
         return (HERE / "_ref" / "libref_gpu.so").exists()
+
+    def set_table(self, table) -> None:
+        table = np.ascontiguousarray(table)
+        rc = self.lib.refgpu_set_table(table.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(table.shape[0]))
+        assert rc == 0
 
     def refine_raw(self, scene, vox, vs):
         vox = np.ascontiguousarray(vox, np.float32).reshape(-1, 3)

@@ -18,18 +18,22 @@
 #include <omp.h>
 #endif
 
+// the two kernel bodies as templates over the SDF functor + the primitive-table functor (reference functions only)
+#include "ref_functor.inc"
+
 namespace {
 template <class Body> void run_grid(unsigned n_threads_total, Body body) {
+    // one loop iteration = one CUDA thread; OpenMP hands out small runs of consecutive threads, so that a launch of a few
+    // hundred voxels still uses every host core (a block-granular split left the CPU arm's bounded samples single-threaded)
     const unsigned nb = (n_threads_total + BLOCK_SIZE - 1) / BLOCK_SIZE;
+    const long long total = (long long) nb * BLOCK_SIZE;
 #pragma omp parallel for schedule(dynamic, 8)
-    for (long long b = 0; b < (long long) nb; b++) {
+    for (long long g = 0; g < total; g++) {
         blockDim = { BLOCK_SIZE, 1, 1 };
         gridDim = { nb, 1, 1 };
-        blockIdx = { (unsigned) b, 0, 0 };
-        for (unsigned t = 0; t < BLOCK_SIZE; t++) {
-            threadIdx = { t, 0, 0 };
-            body();
-        }
+        blockIdx = { (unsigned) (g / BLOCK_SIZE), 0, 0 };
+        threadIdx = { (unsigned) (g % BLOCK_SIZE), 0, 0 };
+        body();
     }
 }
 }  // namespace
@@ -64,6 +68,36 @@ void ref_refine(const float* voxels, unsigned n, const float* voxel_size, float*
 void ref_mesh(const float* voxels, unsigned n, const float* voxel_size, float* out_triangles /* 5n*18 */) {
     VoxelField in { { voxel_size[0], voxel_size[1], voxel_size[2] }, (Point*) voxels, n };
     run_grid(n, [&] { compute_surface_triangles_from_voxel_field_by_sdf(in, (Triangle*) out_triangles); });
+}
+
+// ---- functor templates (ref_functor.inc): scene 1 = sd_obj (must equal the unmodified kernels above byte for byte),
+//      scene 2 = sd_unit_mandelbulb, scene 3 = the SdmPrimitive table fold (e.g. the 1024-primitive scene), un-culled ----
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void) n;
+#endif
+}
+void ref_tpl_refine(int scene, const SdmPrimitive* prims, unsigned count, const float* voxels, unsigned n, const float* voxel_size,
+                    float* out_voxels /* 8n*3 */) {
+    VoxelField in { { voxel_size[0], voxel_size[1], voxel_size[2] }, (Point*) voxels, n };
+    VoxelField out { { 0.0f, 0.0f, 0.0f }, (Point*) out_voxels, n * 8u };
+    if (scene == 1) run_grid(n, [&] { tpl_refine(in, out, SdObj()); });
+    else if (scene == 2) run_grid(n, [&] { tpl_refine(in, out, SdUnitMandelbulb()); });
+    else run_grid(n, [&] { tpl_refine(in, out, SdTable { prims, count }); });
+}
+void ref_tpl_mesh(int scene, const SdmPrimitive* prims, unsigned count, const float* voxels, unsigned n, const float* voxel_size,
+                  float* out_triangles /* 5n*18 */) {
+    VoxelField in { { voxel_size[0], voxel_size[1], voxel_size[2] }, (Point*) voxels, n };
+    if (scene == 1) run_grid(n, [&] { tpl_mesh(in, (Triangle*) out_triangles, SdObj()); });
+    else if (scene == 2) run_grid(n, [&] { tpl_mesh(in, (Triangle*) out_triangles, SdUnitMandelbulb()); });
+    else run_grid(n, [&] { tpl_mesh(in, (Triangle*) out_triangles, SdTable { prims, count }); });
+}
+void ref_tpl_sdf(const SdmPrimitive* prims, unsigned count, const float* p, unsigned n, float* out) {
+    const SdTable sd { prims, count };
+#pragma omp parallel for
+    for (long long i = 0; i < (long long) n; i++) out[i] = sd(vec3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
 }
 
 // ---- primitive-level probes (pin the oracle's restatement function by function) ------------

@@ -100,3 +100,50 @@ def test_header_is_plain_c_and_layouts_match_the_ctypes_mirrors(tmp_path):
         assert int(out[n]) == ctypes.sizeof(c), f"{n}: C says {out[n]} bytes, ctypes mirror has {ctypes.sizeof(c)}"
     assert int(out["SdmPrimitive"]) == bsdmg_b200.scenes.PRIM_DTYPE.itemsize == 40
     assert int(out["SdmTriangle"]) == 72 and int(out["SdmPoint"]) == 12 and int(out["SdmVoxelField"]) == 32   # bindings.h:43-64
+
+
+def _rust_f32(x):
+    """Rust's `{}` for an f32, restated with numpy's Dragon4 (shortest digits that round-trip, positional)."""
+    x = np.float32(x)
+    if np.isnan(x):
+        return "NaN"
+    if np.isinf(x):
+        return "inf" if x > 0 else "-inf"
+    return np.format_float_positional(x, unique=True, trim="-")
+
+
+def test_obj_writer_numbers_and_empty_mesh(tmp_path):
+    """sdm_mesh_save_obj (C ABI, host mesh - no GPU needed): every number is the shortest round-tripping decimal in
+    positional notation (Rust's `{}`), over random bit patterns, powers of two, denormals, +-0, NaN and infinities; an
+    empty mesh writes the header lines only (src/cuda/mod.rs:327-345)."""
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([
+        rng.integers(0, 1 << 32, size=30000, dtype=np.uint64).astype(np.uint32).view(np.float32),
+        rng.uniform(-2.5, 2.5, size=30000).astype(np.float32),
+        np.float32(2.0) ** np.arange(-149, 128, dtype=np.float32),
+        np.float32([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-5, 0.1, 1 / 3, 16777216.0, 3.4028235e38, 1e-45, 1.17549435e-38]),
+    ]).astype(np.float32)
+    vals = np.resize(vals, (len(vals) + 2) // 3 * 3).reshape(-1, 3)
+    m = bsdmg_b200.Mesh(vals, vals[::-1].copy(), np.uint32([[0, 1, 2], [2, 1, 0]]))
+    p = tmp_path / "numbers.obj"
+    m.save_obj(p)
+    lines = p.read_text().splitlines()
+    nv = vals.shape[0]
+    assert len(lines) == 2 * nv + 1 + 2 + 2
+    for i in range(nv):
+        assert lines[i] == "v " + " ".join(_rust_f32(x) for x in vals[i]), (i, vals[i])
+        got = np.array([np.float32(t) for t in lines[i].split()[1:]], np.float32)   # and they read back as the same floats
+        assert np.array_equal(got.view(np.uint32)[~np.isnan(vals[i])], vals[i].view(np.uint32)[~np.isnan(vals[i])])
+    assert lines[nv] == "vt 0 0"
+    assert lines[nv + 1] == "vn " + " ".join(_rust_f32(x) for x in vals[-1])
+    assert lines[-2:] == ["f 1/1/1 2/1/2 3/1/3", "f 3/1/3 2/1/2 1/1/1"]
+    e = bsdmg_b200.Mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    e.save_obj(tmp_path / "empty.obj")
+    assert (tmp_path / "empty.obj").read_text() == "vt 0 0\no default\ng default\n"
+
+
+def test_hash_bytes_is_fnv1a64(oracle_mod):
+    lib = bsdmg_b200.load_library()
+    data = np.random.default_rng(5).integers(0, 256, size=100_003, dtype=np.uint8)
+    assert int(lib.sdm_hash_bytes(data.ctypes.data, data.size)) == oracle_mod.fnv1a64(data)
+    assert int(lib.sdm_hash_bytes(None, 0)) == 0xCBF29CE484222325

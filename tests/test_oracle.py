@@ -161,3 +161,28 @@ def test_oracle_port_matches_reference_at_baseline_config_c2(oracle_mod):
     pos, nrm, idx = o.weld(tris)
     assert (idx.shape[0], pos.shape[0]) == (want["triangles"], want["vertices"])
     assert h(oracle_mod, idx) == want["fnv_indices"] and h(oracle_mod, pos) == want["fnv_positions"] and h(oracle_mod, nrm) == want["fnv_normals"]
+
+
+def test_functor_templates_reproduce_the_reference_kernels(oracle_mod):
+    """oracle/ref_functor.inc: the two kernel bodies re-stated over an SDF functor (needed for every scene but sd_obj, which
+    the reference hard-wires).  With sd_obj they must equal the UNMODIFIED kernels byte for byte; the primitive-table functor
+    (the reference's own sd_box / sd_line / smooth_min in a fold) must equal the CPU port on table scenes."""
+    if not oracle_mod.RefHost.available():
+        pytest.skip("oracle/_ref/libref_host.so not built (reference not mounted at build time)")
+    R = oracle_mod.RefHost()
+    o = oracle_mod.Oracle(scenes.sd_obj())
+    vox, vs = o.create_voxel_field()
+    assert np.array_equal(bits(R.tpl_refine_raw(1, None, vox, vs)), bits(R.refine_raw(vox, vs)))
+    vox, vs = o.refine(vox, vs)
+    assert np.array_equal(bits(R.tpl_mesh_raw(1, None, vox, vs)), bits(R.mesh_raw(vox, vs)))
+    # sd_obj written as a table (BOX_SKELETON + SPHERE) through the table functor = the hard-wired sd_obj
+    assert np.array_equal(bits(R.tpl_mesh_raw(3, scenes.sd_obj(), vox, vs)), bits(R.mesh_raw(vox, vs)))
+    pts = np.random.default_rng(9).uniform(-2.6, 2.6, size=(20000, 3)).astype(np.float32)
+    for table in (scenes.sphere_box(), scenes.many_primitives(64), scenes.many_primitives(1024, t=1.25)):
+        assert np.array_equal(bits(R.tpl_sdf(table, pts)), bits(oracle_mod.Oracle(table).sdf(pts)))
+    table = scenes.many_primitives(64)
+    o = oracle_mod.Oracle(table)
+    vox, vs = o.create_voxel_field(5.0, 16)
+    assert np.array_equal(bits(R.tpl_refine_raw(3, table, vox, vs)), bits(o.refine_raw(vox, vs)))
+    vox, vs = o.refine(vox, vs)
+    assert np.array_equal(bits(R.tpl_mesh_raw(3, table, vox, vs)), bits(o.mesh_raw(vox, vs)[0]))
