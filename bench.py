@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU exchange: device-driven over peer memory, or host-driven over NCCL")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -286,7 +287,19 @@ def main():
 
     from bsdmg_b200 import parallel
 
-    runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist)
+    exchange = "single"
+    if world > 1 and args.exchange == "peer":
+        try:   # device-driven exchange over peer-mapped memory (CUDA IPC); the host-driven NCCL exchange remains as the fallback
+            runner = parallel.PeerRemesher(h, bb, init, levels, rank, world, dist)
+            exchange = "peer (device-side flags, stores over NVLink into rank 0 / per-rank PCIe for e2e)"
+        except Exception as exc:   # noqa: BLE001 - any set-up failure (IPC not permitted, ...) must not lose the measurement
+            print(f"[rank {rank}] peer exchange unavailable ({exc}); using the NCCL exchange", file=sys.stderr, flush=True)
+            runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist)
+            exchange = "nccl (host-driven)"
+    else:
+        runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist)
+        if world > 1:
+            exchange = "nccl (host-driven)"
 
     def barrier():
         torch.cuda.synchronize()
@@ -398,12 +411,14 @@ def main():
             "roofline": roofline, "roofline_hbm": roofline_hbm,
         }
         if world > 1:
-            line["rank0_phase_ms"] = dict(zip(("local_shard_and_weld", "counts_ranges_boundary_keys", "resolve", "gather"), getattr(runner, "last_phases", [])))
+            line["exchange"] = exchange
             line["root_weld_fallback"] = bool(getattr(runner, "last_fallback", False))
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_subvolume_steps(scene_name, scene, bb, init, levels, res, steps=3, warmup=0, target_s=5.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "triangles_per_s")}
         print(json.dumps(line), flush=True)
+    if hasattr(runner, "close"):
+        runner.close()
     h.close()
     if dist is not None:
         dist.barrier()

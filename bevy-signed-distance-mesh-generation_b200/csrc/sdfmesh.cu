@@ -242,6 +242,8 @@ struct SdmHandle {
     float list_delta = 0.0f;           // inflation of the boxes the current records are proven on (= slack of the mesh stage)
     float delta_override = 0.0f;       // > 0: sdm_remesh knows the final voxel size and uses one inflation for all levels
     DevBuf<uint32_t> urec, tri_rec;    // per vertex / per raw triangle: its list record
+    DevBuf<uint4> vrec;                // per vertex: its OWN record (k_vertex_lists)
+    DevBuf<uint32_t> vbin, perm, hist; // binning of the vertices by record: bin per vertex, vertices in bin order, bin counters
     DevBuf<uint32_t> uesc;             // bitmap: vertices that ended outside their record's region
     EdgeLattice lattice {};            // integer lattice of the current field (k_edges' fast keys); enabled = 0: generic keys
     bool lattice_ok = true;            // cleared when a mesh stage reported ERR_LATTICE for the current field
@@ -272,6 +274,18 @@ struct SdmHandle {
     int welded_set = 0, welded_vset = 0;   // output sets holding the local weld's indices / vertices
     uint32_t welded_v = 0, welded_t = 0;   // rows of the local weld (after sdm_shard_apply_remap: kept vertices)
     ShardOffsets res_offsets {};      // vertex / duplicate-pair offsets of the last sdm_shard_resolve
+    // peer exchange (sdm_peer_*): rank 0's control block / row slots / pair lists / second output set - own or IPC-mapped
+    DevBuf<unsigned char> peer_block;
+    PeerCtl* ctl = nullptr;
+    uint4* peer_rows = nullptr;
+    uint2* peer_pairs = nullptr;
+    float *root_pos = nullptr, *root_nrm = nullptr;
+    uint32_t* root_idx = nullptr;
+    uint32_t peer_rank = 0, peer_world = 0, peer_cap_rows = 0, peer_cap_v = 0, peer_cap_t = 0;
+    void* ipc_mapped[4] = { nullptr, nullptr, nullptr, nullptr };
+    DevBuf<PeerLocal> peer_local;
+    PeerLocal* host_peer_local = nullptr;   // pinned
+    int peer_deliver = 0;
     DevBuf<uint32_t> shard_scratch;   // 128 words: x range, counters, per-shard duplicate counts / cursors / offsets
     uint32_t* host_scratch = nullptr; // pinned mirror
     uint32_t own_tris = 0, own_uniq = 0;   // the local shard's counts (sdm_shard_remesh)
@@ -279,10 +293,12 @@ struct SdmHandle {
     bool mesh_valid = false;
 
     // persistent grid sizes
+    int g_vlists = 0;
     int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0, g_edges = 0;
+    uint32_t bin_chunk = 64;            // ... when the vertices are walked in bin order (SDM_BIN_CHUNK)
     uint32_t proj_chunk = 256;          // vertex chunk per warp in k_project (SDM_PROJ_CHUNK overrides)
     float slack_factor = 1.0f;         // inflation of the list regions in units of the child voxel size (SDM_SLACK overrides)
-    bool use_lists = true, use_lattice = true;   // SDM_NO_LISTS / SDM_NO_LATTICE: developer switches for A/B measurements
+    bool use_lists = true, use_lattice = true, use_bins = true;   // SDM_NO_LISTS / SDM_NO_LATTICE / SDM_NO_BINS: developer switches for A/B measurements
 
     SdmStats stats {};
 
@@ -354,6 +370,7 @@ int configure_kernels(SdmHandle* h) {
         { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_cases, 256, &h->g_classify },
         { (const void*) k_project, 128, &h->g_project }, { (const void*) k_vertex_normals, 128, &h->g_normals },
         { (const void*) k_orient, 128, &h->g_orient },   { (const void*) k_project_tail, 128, &h->g_tail },
+        { (const void*) k_vertex_lists, 128, &h->g_vlists },
     };
     for (const K& k : ks) {
         const size_t smem = smem_for(h, k.threads);
@@ -424,6 +441,10 @@ int reserve_all(SdmHandle* h, uint32_t cap_vox, uint32_t cap_tris, uint32_t cap_
     for (int i = 0; i < 2; i++) { CK(h->vl[i].reserve((size_t) cap_vox * 2)); CK(h->vparent[i].reserve(cap_vox)); }
     CK(h->tri_rec.reserve(cap_tris));
     CK(h->urec.reserve(cap_uniq));
+    CK(h->vrec.reserve((size_t) cap_uniq * 2));
+    CK(h->vbin.reserve(cap_uniq));
+    CK(h->perm.reserve(cap_uniq));
+    CK(h->hist.reserve(SDM_BINS));
     CK(h->uesc.reserve((size_t) cap_uniq / 32 + 32));
     CK(h->m27.reserve(cap_vox));
     CK(h->tri_off.reserve(cap_vox));
@@ -602,10 +623,24 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
+    // per-vertex records + binning: the per-vertex kernels then walk the vertices in bin order with warp-uniform lists
+    const bool bins = lists && h->use_bins;
+    const uint4* vlv = bins ? h->vrec.p : vl;
+    const uint32_t* perm = bins ? h->perm.p : nullptr;
+    if (bins) {
+        NvtxRange nv(h, "mesh: vertex records + binning");
+        CK(dev_fill(s, h->hist.p, 0, (size_t) SDM_BINS * 4));
+        k_vertex_lists<<<h->g_vlists, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->cap_uniq, h->grid, vl, h->urec.p, h->vrec.p, h->vbin.p, h->hist.p, h->list_delta);
+        mark(h, "k_vertex_lists");
+        k_bin_scan<<<1, 1024, 0, s>>>(h->hist.p);
+        k_bin_scatter<<<h->g_light, 256, 0, s>>>(h->state.p, h->cap_uniq, h->vbin.p, h->hist.p, h->perm.p);
+        mark(h, "k_bin_scan+scatter");
+        h->stats.kernel_launches += 4;
+    }
     {
         NvtxRange nv(h, "mesh: project");
         k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid,
-                                                     h->proj_chunk, vl, h->urec.p, h->uesc.p, slack2);
+                                                     bins ? h->bin_chunk : h->proj_chunk, vlv, h->urec.p, h->uesc.p, slack2, perm);
         mark(h, "k_project");
         k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid, h->ustart.p,
                                                        vl ? h->uesc.p : nullptr, slack2);
@@ -614,7 +649,7 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     {
         NvtxRange nv(h, "mesh: vertex normals + weld keys");
         k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid,
-                                                            fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p, vl, h->urec.p, h->uesc.p);
+                                                            fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p, vlv, h->urec.p, h->uesc.p, perm);
         mark(h, "k_vertex_normals");
     }
     {
@@ -795,9 +830,11 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         cudaMemcpyToSymbolAsync(c_mc_ntri, SDM_MC_NTRI_INIT, sizeof(SDM_MC_NTRI_INIT), 0, cudaMemcpyHostToDevice, h->stream);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, std::string("init: ") + cudaGetErrorString(cudaGetLastError())); break; }
         if (const char* e = getenv("SDM_SLACK")) { const float v = (float) atof(e); if (v > 0.0f && v <= 8.0f) h->slack_factor = v; }
+        if (const char* e = getenv("SDM_BIN_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->bin_chunk = (uint32_t) v & ~31u; }
         if (const char* e = getenv("SDM_PROJ_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->proj_chunk = (uint32_t) v & ~31u; }
         h->use_lists = getenv("SDM_NO_LISTS") == nullptr;
         h->use_lattice = getenv("SDM_NO_LATTICE") == nullptr;
+        h->use_bins = getenv("SDM_NO_BINS") == nullptr;
         SdmPrimitive def[2];
         sdm_scene_default(def, 2);
         rc = sdm_set_scene(h, def, 2);
@@ -822,10 +859,13 @@ void sdm_destroy(SdmHandle* h) {
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
     h->entry_uid.release(); h->vidx.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release();
     for (int i = 0; i < 2; i++) { h->vl[i].release(); h->vparent[i].release(); }
-    h->urec.release(); h->tri_rec.release(); h->uesc.release(); h->stragglers.release(); h->state.release();
+    h->urec.release(); h->tri_rec.release(); h->uesc.release(); h->vrec.release(); h->vbin.release(); h->perm.release(); h->hist.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     if (h->host_scratch) cudaFreeHost(h->host_scratch);
+    if (h->host_peer_local) cudaFreeHost(h->host_peer_local);
+    for (void* m : h->ipc_mapped) if (m) cudaIpcCloseMemHandle(m);
+    h->peer_block.release(); h->peer_local.release();
     h->shard_scratch.release();
     h->shard_range.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -1622,6 +1662,238 @@ int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangl
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->stats.last_gpu_ms = ms;
     mesh_view(h, out_mesh);
+    return SDM_OK;
+}
+
+
+// ---- peer exchange -------------------------------------------------------------------------------------------------------------
+int sdm_reserve(SdmHandle* h, uint32_t voxel_capacity) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    uint32_t want = 0;
+    int rc = capacity_for(h, voxel_capacity, &want);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return ensure_capacity(h, want);
+}
+
+static size_t peer_rows_offset() { return (sizeof(PeerCtl) + 255) & ~(size_t) 255; }
+static size_t peer_pairs_offset(uint32_t world, uint32_t cap_rows) { return peer_rows_offset() + (size_t) 2 * world * cap_rows * sizeof(uint4); }
+static size_t peer_block_bytes(uint32_t world, uint32_t cap_rows) { return peer_pairs_offset(world, cap_rows) + (size_t) 2 * world * cap_rows * sizeof(uint2); }
+static int peer_common_alloc(SdmHandle* h) {
+    CK(h->peer_local.reserve(1));
+    if (!h->host_peer_local) CK(cudaMallocHost(&h->host_peer_local, sizeof(PeerLocal)));
+    return ensure_shard_scratch(h);
+}
+
+int sdm_peer_root_export(SdmHandle* h, uint32_t world, uint32_t cap_rows, SdmPeerExport* out) {
+    if (!h || !out) return fail(SDM_ERR_INVALID, "null argument");
+    if (world == 0 || world > SDM_PEER_MAX || cap_rows == 0) return fail(SDM_ERR_INVALID, "1..32 ranks, cap_rows > 0");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t bytes = peer_block_bytes(world, cap_rows);
+    CK(h->peer_block.reserve(bytes));
+    CK(cudaMemset(h->peer_block.p, 0, bytes));
+    memset(out, 0, sizeof(*out));
+    const void* ptrs[4] = { h->peer_block.p, h->out_pos[1].p, h->out_nrm[1].p, h->out_idx[1].p };
+    for (int i = 0; i < 4; i++) {
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, const_cast<void*>(ptrs[i])));
+        static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(out->handle[i], &mh, 64);
+    }
+    out->block_bytes = bytes; out->cap_vertices = h->cap_uniq; out->cap_triangles = h->cap_tris; out->cap_rows = cap_rows; out->world = world;
+    return SDM_OK;
+}
+
+int sdm_peer_attach(SdmHandle* h, const SdmPeerExport* root, uint32_t rank, uint32_t world, SdmHandle* same_process_root) {
+    if (!h || !root) return fail(SDM_ERR_INVALID, "null argument");
+    if (world != root->world || rank >= world) return fail(SDM_ERR_INVALID, "rank / world do not match the export");
+    CK(cudaSetDevice(h->device));
+    int rc = peer_common_alloc(h);
+    if (rc) return rc;
+    void* base[4] = { nullptr, nullptr, nullptr, nullptr };
+    if (rank == 0) {
+        base[0] = h->peer_block.p; base[1] = h->out_pos[1].p; base[2] = h->out_nrm[1].p; base[3] = h->out_idx[1].p;
+    } else if (same_process_root) {
+        base[0] = same_process_root->peer_block.p; base[1] = same_process_root->out_pos[1].p; base[2] = same_process_root->out_nrm[1].p;
+        base[3] = same_process_root->out_idx[1].p;
+    } else {
+        for (int i = 0; i < 4; i++) {
+            if (h->ipc_mapped[i]) { cudaIpcCloseMemHandle(h->ipc_mapped[i]); h->ipc_mapped[i] = nullptr; }
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, root->handle[i], 64);
+            CK(cudaIpcOpenMemHandle(&h->ipc_mapped[i], mh, cudaIpcMemLazyEnablePeerAccess));
+            base[i] = h->ipc_mapped[i];
+        }
+    }
+    if (!base[0]) return fail(SDM_ERR_STATE, "rank 0 has not exported yet");
+    unsigned char* b0 = reinterpret_cast<unsigned char*>(base[0]);
+    h->ctl = reinterpret_cast<PeerCtl*>(b0);
+    h->peer_rows = reinterpret_cast<uint4*>(b0 + peer_rows_offset());
+    h->peer_pairs = reinterpret_cast<uint2*>(b0 + peer_pairs_offset(world, root->cap_rows));
+    h->root_pos = reinterpret_cast<float*>(base[1]); h->root_nrm = reinterpret_cast<float*>(base[2]); h->root_idx = reinterpret_cast<uint32_t*>(base[3]);
+    h->peer_rank = rank; h->peer_world = world; h->peer_cap_rows = root->cap_rows; h->peer_cap_v = root->cap_vertices; h->peer_cap_t = root->cap_triangles;
+    return SDM_OK;
+}
+
+int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, uint32_t epoch, int deliver, uint32_t phase_mask, int spin) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    if (!h->ctl) return fail(SDM_ERR_STATE, "sdm_peer_attach first");
+    SdmParams p { SDM_MESH_GENERATION_BB_SIZE, SDM_MESH_GENERATION_INIT_FACTOR, 0 };
+    if (params) p = *params;
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (split_level > p.levels) split_level = p.levels;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const uint32_t rank = h->peer_rank, world = h->peer_world, par = epoch & 1u, cap_rows = h->peer_cap_rows;
+    PeerCtl* ctl = h->ctl;
+    uint4* my_rows = h->peer_rows + ((size_t) par * world + rank) * cap_rows;
+    const uint4* all_rows = h->peer_rows + (size_t) par * world * cap_rows;
+    uint2* pairs = h->peer_pairs + (size_t) par * world * cap_rows;
+    uint32_t* counter = h->shard_scratch.p + 3;
+    h->peer_deliver = deliver;
+    if (phase_mask & 1u) {   // P0: this rank's shard, welded locally; header to rank 0
+        NvtxRange nv(h, "peer P0: shard + local weld");
+        if ((uint64_t) p.init_factor * p.init_factor * p.init_factor > h->cap_vox) return fail(SDM_ERR_CAPACITY, "sdm_reserve first");
+        prof_begin(h);
+        CK(cudaEventRecord(h->ev0, s));
+        rc = reset_state(h);
+        if (rc) return rc;
+        mark(h, "start");
+        rc = enqueue_init_field(h, p);
+        if (rc) return rc;
+        h->delta_override = h->slack_factor * ldexpf(p.bb_size / (float) p.init_factor, -(int) p.levels);
+        for (uint32_t l = 0; l < split_level && !rc; l++) rc = enqueue_refine(h);
+        if (rc) { h->delta_override = 0.0f; return rc; }
+        {
+            const bool vp = h->lists_level == h->level;
+            k_take_shard<<<h->g_light, 256, 0, s>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, rank, world, h->shard_range.p,
+                                                     vp ? h->vparent[h->vp_cur].p : nullptr, vp ? h->vparent[h->vp_cur ^ 1].p : nullptr);
+            k_set_level_count<<<1, 1, 0, s>>>(h->state.p, h->level, h->shard_range.p);
+            mark(h, "k_take_shard");
+            h->stats.kernel_launches += 2;
+            h->cur ^= 1;
+            if (vp) h->vp_cur ^= 1;
+        }
+        for (uint32_t l = split_level; l < p.levels && !rc; l++) rc = enqueue_refine(h, l + 1 == p.levels);
+        h->delta_override = 0.0f;
+        if (rc) return rc;
+        rc = enqueue_mesh_local(h, true);
+        if (rc) return rc;
+        h->out_sel = 0;   // set 0: the local weld; set 1: this rank's final rows (on rank 0 with deliver = 0: the merged mesh)
+        rc = enqueue_weld(h, true);
+        if (rc) return rc;
+        k_shard_scratch_init<<<1, 32, 0, s>>>(h->shard_scratch.p);
+        k_shard_xrange<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[0].p, h->shard_scratch.p);
+        k_peer_publish_header<<<1, 32, 0, s>>>(h->state.p, h->shard_scratch.p, ctl, rank, par);
+        k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagA[rank], epoch);
+        mark(h, "peer_header");
+        h->stats.kernel_launches += 4;
+    }
+    if (phase_mask & 2u) {   // P1: key rows of the vertices inside another shard's x range -> this rank's slot on rank 0
+        NvtxRange nv(h, "peer P1: interface key rows");
+        if (spin) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagA, world, epoch);
+        k_peer_rows<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[0].p, ctl, rank, world, par, my_rows, cap_rows, counter);
+        k_peer_publish_rows<<<1, 32, 0, s>>>(counter, ctl, rank, par, cap_rows);
+        k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagB[rank], epoch);
+        mark(h, "peer_rows");
+        h->stats.kernel_launches += 3 + (spin ? 1 : 0);
+    }
+    if ((phase_mask & 4u) && rank == 0) {   // P2: owners, removal bitmap, offsets, pairs
+        NvtxRange nv(h, "peer P2: resolve");
+        if (spin) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagB, world, epoch);
+        const uint32_t entries = std::min<uint32_t>(pow2_at_least(std::max<uint64_t>((uint64_t) world * cap_rows * 2, 1024)), h->table_entries);
+        if ((uint64_t) entries * 4 < (uint64_t) world * cap_rows * 5 || (uint64_t) world * cap_rows > h->wref.n)
+            return fail(SDM_ERR_CAPACITY, "rank 0's tables are too small for world x cap_rows key rows");
+        k_peer_root_offsets<<<1, 32, 0, s>>>(ctl, world, par, h->cap_uniq, h->cap_tris);
+        CK(dev_fill(s, h->first_bits.p, 0, ((size_t) h->cap_uniq / 32 + 2) * 4));
+        CK(dev_fill(s, h->table2.p, 0xFF, (size_t) entries * 16));
+        k_peer_res_insert<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, entries - 1, h->wref.p, &ctl->status[par]);
+        k_peer_res_mark<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, h->wref.p, h->first_bits.p);
+        k_scan_bits_1block_dev<<<1, 1024, 0, s>>>(h->first_bits.p, h->first_prefix.p, &ctl->voff[par][world]);
+        k_peer_root_goff<<<1, 32, 0, s>>>(ctl, world, par);
+        k_peer_res_pairs<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p, pairs);
+        if (deliver == 0) CK(cudaStreamWaitEvent(s, h->ev_copy_done[1], 0));   // the peers are about to overwrite the set a download may still read
+        k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagC, epoch);
+        mark(h, "peer_resolve");
+        h->stats.kernel_launches += 9 + (spin ? 1 : 0);
+    }
+    if (phase_mask & 8u) {   // P3: drop own duplicates, global indices, rows to their final place
+        NvtxRange nv(h, "peer P3: apply + deliver");
+        if (spin) k_peer_wait<<<1, 32, 0, s>>>(&ctl->flagC, 1, epoch);
+        if (deliver != 0 || rank == 0) CK(cudaStreamWaitEvent(s, h->ev_copy_done[1], 0));
+        CK(dev_fill(s, h->tri_valid_bits.p, 0, ((size_t) h->cap_uniq / 32 + 2) * 4));
+        k_peer_apply_mark<<<h->g_light, 256, 0, s>>>(ctl, rank, par, pairs, h->tri_valid_bits.p, h->vidx.p, h->peer_local.p);
+        k_scan_bits_1block_dev<<<1, 1024, 0, s>>>(h->tri_valid_bits.p, h->tri_prefix.p, &ctl->hdr[par][rank].V);
+        const bool global = deliver == 0;
+        float* dpos = global ? h->root_pos : h->out_pos[1].p;
+        float* dnrm = global ? h->root_nrm : h->out_nrm[1].p;
+        uint32_t* didx = global ? h->root_idx : h->out_idx[1].p;
+        k_peer_apply_vertices<<<h->g_light * 2, 256, 0, s>>>(ctl, rank, par, h->tri_valid_bits.p, h->tri_prefix.p, h->out_pos[0].p, h->out_nrm[0].p, dpos, dnrm, global ? 1u : 0u);
+        k_peer_apply_indices<<<h->g_light * 2, 256, 0, s>>>(ctl, rank, par, h->tri_valid_bits.p, h->tri_prefix.p, h->vidx.p, h->out_idx[0].p, didx, global ? 1u : 0u);
+        k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagD[rank], epoch);
+        mark(h, "peer_apply");
+        h->stats.kernel_launches += 6 + (spin ? 1 : 0);
+    }
+    if (phase_mask & 16u) {   // P4: rank 0 waits for everybody's rows; totals for the host
+        if (spin && rank == 0) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagD, world, epoch);
+        k_peer_totals<<<1, 32, 0, s>>>(ctl, world, par, h->peer_local.p);
+        CK(cudaEventRecord(h->ev1, s));
+        CK(cudaEventRecord(h->ev_mesh_done[1], s));
+        h->stats.kernel_launches += 1 + ((spin && rank == 0) ? 1 : 0);
+    }
+    CK(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_peer_finish(SdmHandle* h, SdmPeerResult* out, SdmMesh* out_mesh) {
+    if (!h || !out) return fail(SDM_ERR_INVALID, "null argument");
+    if (!h->ctl) return fail(SDM_ERR_STATE, "sdm_peer_attach first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->host_peer_local, h->peer_local.p, sizeof(PeerLocal), cudaMemcpyDeviceToHost, h->stream));
+    uint32_t flags = 0;
+    int rc = fetch_state(h, &flags);
+    if (rc) return rc;
+    const PeerLocal& L = *h->host_peer_local;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_gpu_ms = ms;
+    fill_stats(h, true);
+    prof_end(h);
+    memset(out, 0, sizeof(*out));
+    out->status = L.status | flags; out->gpu_ms = ms;
+    out->total_vertices = L.total_V; out->total_triangles = L.total_T;
+    out->vertex_offset = L.goff; out->triangle_offset = L.toff; out->vertices = L.kept; out->triangles = L.T;
+    if (out->status) {
+        if ((out->status & 0xFFu) == ERR_HASH_FULL) h->table1_entries = h->table_entries;
+        if ((out->status & 0xFFu) == ERR_LATTICE) { h->lattice_ok = false; h->lat_fail_bb = h->field_bb; h->lat_fail_init = h->field_init; }
+        char buf[96];
+        snprintf(buf, sizeof buf, "peer step failed on some rank: status 0x%x (capacity / table / non-finite vertices)", out->status);
+        return fail(SDM_ERR_CAPACITY, buf);
+    }
+    adapt_table1(h);
+    if (out_mesh) {
+        const bool merged = h->peer_deliver == 0 && h->peer_rank == 0;
+        out_mesh->positions = h->out_pos[1].p; out_mesh->normals = h->out_nrm[1].p; out_mesh->indices = h->out_idx[1].p;
+        out_mesh->vertex_count = merged ? L.total_V : (h->peer_deliver ? L.kept : 0u);
+        out_mesh->triangle_count = merged ? L.total_T : (h->peer_deliver ? L.T : 0u);
+        out_mesh->on_device = 1; out_mesh->reserved = 1;
+    }
+    return SDM_OK;
+}
+
+int sdm_peer_download_async(SdmHandle* h, const SdmPeerResult* r, float* host_positions, float* host_normals, uint32_t* host_indices) {
+    if (!h || !r) return fail(SDM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t cs = h->copy_stream;
+    CK(cudaStreamWaitEvent(cs, h->ev_mesh_done[1], 0));
+    if (r->vertices && host_positions) CK(cudaMemcpyAsync(host_positions + 3 * (size_t) r->vertex_offset, h->out_pos[1].p, (size_t) r->vertices * 12, cudaMemcpyDeviceToHost, cs));
+    if (r->vertices && host_normals) CK(cudaMemcpyAsync(host_normals + 3 * (size_t) r->vertex_offset, h->out_nrm[1].p, (size_t) r->vertices * 12, cudaMemcpyDeviceToHost, cs));
+    if (r->triangles && host_indices) CK(cudaMemcpyAsync(host_indices + 3 * (size_t) r->triangle_offset, h->out_idx[1].p, (size_t) r->triangles * 12, cudaMemcpyDeviceToHost, cs));
+    CK(cudaEventRecord(h->ev_copy_done[1], cs));
+    (void) cudaStreamQuery(cs);
     return SDM_OK;
 }
 

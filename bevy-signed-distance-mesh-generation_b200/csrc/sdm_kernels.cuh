@@ -165,10 +165,11 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
         // evaluation points - Newton iterates, stencil points, centroids - may leave the voxel by up to delta).  Candidates: the
         // union of the records the lanes inherited from THEIR parents, else the cell masks.
         if (neval && sc.wmask) {
-            const float lx = bx - delta, ly = by - delta, lz = bz - delta;
-            const float hx = bx + 2.0f * osx + delta, hy = by + 2.0f * osy + delta, hz = bz + 2.0f * osz + delta;
-            uint16_t* own = (vl_out && eval) ? reinterpret_cast<uint16_t*>(vl_out + 2 * (size_t) (p0 + lane)) : nullptr;
-            const float pad = vl_out ? 0.0021f : 0.0f;   // the mesh stage also evaluates the empirical_normal stencil (reach 2e-3)
+            // tile list: the lanes' parent boxes as they are (the 27 lattice points lie inside); own record: the same boxes inflated
+            // by delta (+ the empirical_normal stencil reach of the mesh stage, 2e-3) - one pass over the candidates decides both
+            const float lx = bx, ly = by, lz = bz;
+            const float hx = bx + 2.0f * osx, hy = by + 2.0f * osy, hz = bz + 2.0f * osz;
+            uint16_t* own = vl_out ? reinterpret_cast<uint16_t*>(vl_out + 2 * (size_t) (p0 + lane)) : nullptr;   // warp-uniform null / non-null
             uint32_t ncand = SDM_TLIST_NONE;
             if (vl_in) {
                 uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = lo;
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
                 }
                 ncand = tile_union_lists(sc, lo, hi);
             }
-            if (ncand != SDM_TLIST_NONE) tile_refine(sc, ncand, eval, lx, ly, lz, hx, hy, hz, pad, own);
-            else tile_mask_from_box(grid, sc, eval, lx, ly, lz, hx, hy, hz, own, pad);
+            if (ncand != SDM_TLIST_NONE) tile_refine(sc, ncand, eval, lx, ly, lz, hx, hy, hz, 0.0f, own, delta, 0.0021f);
+            else tile_mask_from_box(grid, sc, eval, lx, ly, lz, hx, hy, hz, own, delta, 0.0021f);
         }
         if (neval) work += (unsigned long long) tile_prims(sc) * 27u * neval;
         uint32_t m27 = 0;
@@ -401,11 +402,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // Fast vertex keys.  On a dyadic grid (the default 5 / 2^k one, any grid whose coordinates are exact multiples of half a voxel)
 // an edge mid-point is identified by three integers, its coordinates in units of half a voxel, so a table entry is ONE 64-bit
-// word (key + 1; 0 = empty) claimed with a 64-bit CAS, and entries of neighbouring mid-points are placed next to each other:
-// the 8^3 half-unit cube a key lies in selects a bucket of 64 entries (512 B), its position inside the cube the entry.
-// Voxels that are neighbours in space are neighbours in the list (children follow their parent), so a bucket is filled by one
-// thread block while it sits in L2.  (The generic table - 16-byte entries keyed by the float bits, scattered by a hash - moved
-// 1.5 GB through DRAM for 135 MB of keys: ncu, profiles/.)
+// word (key + 1; 0 = empty) claimed with a 64-bit CAS - half the table of the generic path (16-byte entries keyed by the float
+// bits), which moved 1.5 GB through DRAM for 135 MB of keys (ncu, profiles/).  A tile first de-duplicates its keys in SHARED
+// memory (an edge is used by up to four voxels, most of them neighbours in the list and hence in the tile), so only one thread
+// per distinct key of the tile goes to the global table: ~2.5x fewer global probes, and almost no CAS contention.
+// (Placing neighbouring keys next to each other in the global table - one 512-byte bucket per 4^3 voxels - was tried and is 4x
+// SLOWER: a tile then hammers a handful of L2 lines instead of spreading over all slices; profiles/r2a_*.)
 // Exactness: the kernel CHECKS, for every voxel and axis, that base, base + size and their mid-point are bit-equal to
 // o + n * half for the integers n it uses; equal keys then imply bit-equal mid-points, which is all the de-duplication needs
 // (two equal mid-points with different keys would merely be projected twice and merged by the weld, like in the reference).
@@ -428,12 +430,10 @@ __device__ __forceinline__ void edge_lattice_offset(int e, int& dx, int& dy, int
     const int x1 = ((c1 & 3) == 1 || (c1 & 3) == 2) ? 2 : 0, y1 = ((c1 & 3) >= 2) ? 2 : 0, z1 = (c1 >= 4) ? 2 : 0;
     dx = (x0 + x1) >> 1; dy = (y0 + y1) >> 1; dz = (z0 + z1) >> 1;
 }
-__device__ __forceinline__ uint32_t lattice_slot(uint32_t ux, uint32_t uy, uint32_t uz, uint32_t mask) {
-    const uint32_t h = hash96(ux >> 3, uy >> 3, uz >> 3);
-    uint32_t l = (ux & 7u) | ((uy & 7u) << 3) | ((uz & 7u) << 6);
-    l = (l * 0x9E5u) >> 5;
-    return ((h << 6) | (l & 63u)) & mask;
+__device__ __forceinline__ unsigned long long lattice_key(int ux, int uy, int uz) {
+    return 1ull + ((unsigned long long) (uint32_t) ux | ((unsigned long long) (uint32_t) uy << 21) | ((unsigned long long) (uint32_t) uz << 42));
 }
+__device__ __forceinline__ uint32_t hash_key64(unsigned long long k) { return hash96((uint32_t) k, (uint32_t) (k >> 32), 0x9E3779B9u); }
 // find-or-insert of a 64-bit key (never 0) from `pos`; returns the entry, *won = this call created it; 0xFFFFFFFF = table full
 __device__ __forceinline__ uint32_t hash64_probe_from(unsigned long long* table, uint32_t mask, uint32_t pos, unsigned long long key, bool* won) {
     for (uint32_t probe = 0; probe <= mask; probe++) {
@@ -455,6 +455,7 @@ __device__ __forceinline__ uint32_t hash64_probe_from(unsigned long long* table,
 // kernels need (coherent neighbourhoods for their primitive lists, coalesced loads).  The id numbering is internal: output
 // order comes from the weld (first occurrence in triangle order), not from here.  For every created vertex: its start point
 // (mid-point, marching_cubes.cu:13-16), its list record (the creating voxel's parent) and the id in the entry's side array.
+#define SDM_EDGE_SLOTS 2048u   /* shared-memory key slots per tile (256 voxels x ~4 edges, ~2.5 uses per key) */
 template <bool LATTICE>
 __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, DevState* st, int level, const uint8_t* __restrict__ cases,
                                                const uint32_t* __restrict__ tri_off, void* table_raw, uint32_t table_mask,
@@ -463,6 +464,8 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
                                                EdgeLattice lat, float sx, float sy, float sz, uint32_t cap_uniq) {
     __shared__ McShared mc;
     __shared__ uint32_t s_eref[12 * 256];   // [edge][thread]: bank-conflict-free dynamic indexing by edge
+    __shared__ unsigned long long s_key[LATTICE ? SDM_EDGE_SLOTS : 1];   // the tile's distinct keys
+    __shared__ uint32_t s_gpos[LATTICE ? SDM_EDGE_SLOTS : 1];            // their global entries (bit 31: this tile created the entry)
     __shared__ uint32_t s_w[9];
     __shared__ uint32_t s_tile, s_base;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -479,6 +482,8 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[TK_EDGES], 1u);
+        if (LATTICE)
+            for (uint32_t i = threadIdx.x; i < SDM_EDGE_SLOTS; i += blockDim.x) s_key[i] = 0ull;
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= ntiles) break;
@@ -487,53 +492,88 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
         const uint32_t emask = mc.edgemask[cube_index];   // case 0 uses no edge
         uint32_t won_mask = 0;
         float bx = 0.f, by = 0.f, bz = 0.f;
-        int nx = 0, ny = 0, nz = 0;
-        if (emask) {
-            bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2];
-            if (LATTICE) {
+        if (LATTICE) {
+            // phase 1: the voxel's keys into the tile's shared-memory table; own_mask = keys this thread put there first.
+            // A key that finds the shared table full goes to the global table directly (s_eref bit 31).
+            uint32_t own_mask = 0;
+            int nx = 0, ny = 0, nz = 0;
+            if (emask) {
+                bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2];
                 const bool ok = lattice_axis(bx, sx, lat.ox, lat.hx, lat.ihx, nx) & lattice_axis(by, sy, lat.oy, lat.hy, lat.ihy, ny) &
                                 lattice_axis(bz, sz, lat.oz, lat.hz, lat.ihz, nz);
                 if (!ok) { off_lattice = true; nx = ny = nz = 0; }
+                for (uint32_t m = emask; m; m &= m - 1u) {
+                    const int e = __ffs((int) m) - 1;
+                    int dx, dy, dz;
+                    edge_lattice_offset(e, dx, dy, dz);
+                    const unsigned long long key = lattice_key(nx + dx, ny + dy, nz + dz);
+                    uint32_t p = hash_key64(key) >> 8 & (SDM_EDGE_SLOTS - 1u), ref = 0xFFFFFFFFu;
+                    for (uint32_t probe = 0; probe < 64u; probe++) {
+                        unsigned long long cur = s_key[p];
+                        if (cur == 0ull) {
+                            cur = atomicCAS(&s_key[p], 0ull, key);
+                            if (cur == 0ull) { own_mask |= 1u << e; ref = p; break; }
+                        }
+                        if (cur == key) { ref = p; break; }
+                        p = (p + 1u) & (SDM_EDGE_SLOTS - 1u);
+                    }
+                    if (ref == 0xFFFFFFFFu) {   // crowded shared table (pathological tile): straight to the global table
+                        bool w;
+                        const uint32_t gp = hash64_probe_from(table8, table_mask, hash_key64(key) & table_mask, key, &w);
+                        if (gp == 0xFFFFFFFFu) { full = true; w = false; }
+                        if (w) won_mask |= 1u << e;
+                        ref = 0x80000000u | (gp & 0x7FFFFFFFu);
+                    }
+                    s_eref[e * 256 + threadIdx.x] = ref;
+                }
+                // phase 2a: start the global table lines of the keys this thread owns on their way
+                for (uint32_t m = own_mask; m; m &= m - 1u) {
+                    const int e = __ffs((int) m) - 1;
+                    prefetch_l2(table8 + (hash_key64(s_key[s_eref[e * 256 + threadIdx.x]]) & table_mask));
+                }
+                // phase 2b: one global find-or-insert per distinct key of the tile
+                for (uint32_t m = own_mask; m; m &= m - 1u) {
+                    const int e = __ffs((int) m) - 1;
+                    const uint32_t p = s_eref[e * 256 + threadIdx.x];
+                    const unsigned long long key = s_key[p];
+                    bool w;
+                    const uint32_t gp = hash64_probe_from(table8, table_mask, hash_key64(key) & table_mask, key, &w);
+                    if (gp == 0xFFFFFFFFu) { full = true; w = false; }
+                    if (w) won_mask |= 1u << e;
+                    s_gpos[p] = gp & 0x7FFFFFFFu;
+                }
             }
-            // Both passes walk the set bits of the case's edge mask (4 edges on average).
+            __syncthreads();
+            // phase 3: every use of a key learns its global entry
+            if (emask)
+                for (uint32_t m = emask; m; m &= m - 1u) {
+                    const int e = __ffs((int) m) - 1;
+                    const uint32_t ref = s_eref[e * 256 + threadIdx.x];
+                    s_eref[e * 256 + threadIdx.x] = (ref & 0x80000000u) ? (ref & 0x7FFFFFFFu) : s_gpos[ref];
+                }
+        } else if (emask) {
+            bx = vox[3 * (size_t) v]; by = vox[3 * (size_t) v + 1]; bz = vox[3 * (size_t) v + 2];
             // pass 1: start the table lines of all used edges on their way (the probes below are dependent chains)
             for (uint32_t m = emask; m; m &= m - 1u) {
                 const int e = __ffs((int) m) - 1;
-                uint32_t pos0;
-                if (LATTICE) {
-                    int dx, dy, dz;
-                    edge_lattice_offset(e, dx, dy, dz);
-                    pos0 = lattice_slot((uint32_t) (nx + dx), (uint32_t) (ny + dy), (uint32_t) (nz + dz), table_mask);
-                    prefetch_l2(table8 + pos0);
-                } else {
-                    float mx, my, mz;
-                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                    uint32_t kx = __float_as_uint(mx);
-                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
-                    pos0 = hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask;
-                    prefetch_l2(table16 + pos0);
-                }
+                float mx, my, mz;
+                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                uint32_t kx = __float_as_uint(mx);
+                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;
+                const uint32_t pos0 = hash96(kx, __float_as_uint(my), __float_as_uint(mz)) & table_mask;
+                prefetch_l2(table16 + pos0);
                 s_eref[e * 256 + threadIdx.x] = pos0;
             }
             // pass 2: find-or-insert from the stored start position; remember the entry per edge and which ones this voxel created
             for (uint32_t m = emask; m; m &= m - 1u) {
                 const int e = __ffs((int) m) - 1;
+                float mx, my, mz;
+                edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
+                uint32_t kx = __float_as_uint(mx);
+                if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
                 bool w;
-                uint32_t pos;
-                if (LATTICE) {
-                    int dx, dy, dz;
-                    edge_lattice_offset(e, dx, dy, dz);
-                    const unsigned long long key = 1ull + ((unsigned long long) (uint32_t) (nx + dx) | ((unsigned long long) (uint32_t) (ny + dy) << 21) |
-                                                           ((unsigned long long) (uint32_t) (nz + dz) << 42));
-                    pos = hash64_probe_from(table8, table_mask, s_eref[e * 256 + threadIdx.x], key, &w);
-                } else {
-                    float mx, my, mz;
-                    edge_midpoint(bx, by, bz, sx, sy, sz, e, mx, my, mz);
-                    uint32_t kx = __float_as_uint(mx);
-                    if (kx == 0xFFFFFFFFu) kx = 0x7FC00000u;   // keep the all-ones EMPTY pattern unreachable
-                    pos = hash_probe_from(table16, table_mask, s_eref[e * 256 + threadIdx.x], kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
-                }
-                if (pos == 0xFFFFFFFFu) { full = true; w = false; }
+                uint32_t pos = hash_probe_from(table16, table_mask, s_eref[e * 256 + threadIdx.x], kx, __float_as_uint(my), __float_as_uint(mz), 0xFFFFFFFEu, &w);
+                if (pos == 0xFFFFFFFFu) { full = true; w = false; pos = 0; }
                 if (w) won_mask |= 1u << e;
                 s_eref[e * 256 + threadIdx.x] = pos;
             }
@@ -616,6 +656,71 @@ __global__ void __launch_bounds__(256) k_clear_weld_state(DevState* st, uint32_t
     if (tid == 0) { st->n_tris_out = 0; st->n_verts_out = 0; st->ticket[TK_SCAN_FIRST] = 0; st->ticket[TK_SCAN_TRI] = 0; st->ticket[TK_PROJECT] = 0; st->n_stragglers = 0; st->ticket[TK_TAIL] = 0; st->weld_dups = 0; }
 }
 
+// ---- per-vertex lists and binning (culled scenes) ------------------------------------------------------------------------------
+// A warp folds the UNION of its lanes' lists, so a lane pays for primitives only its neighbours need: with vertices taken in list
+// order the union is about twice a lane's own need-list.  Here every vertex gets its own record - the exact per-lane test on the
+// ball (start point, slack + stencil reach), candidates from the records of the voxels that created the tile's vertices - and
+// the vertices are then BINNED by record: k_project / k_vertex_normals walk them in bin order, so the lanes of a warp mostly hold
+// the same record and the union is what each lane needs anyway.  Order does not matter to the result: every vertex is projected
+// from its own start point, and output order is decided by the weld.  (Counting sort by a 16-bit hash of the record: histogram
+// here, k_bin_scan, k_bin_scatter; equal records share a bin, the order inside a bin is whatever the atomics give.)
+#define SDM_BINS 65536u
+__global__ void __launch_bounds__(128, 8) k_vertex_lists(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart, uint32_t cap_uniq,
+                                                         MaskGrid grid, const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, uint4* __restrict__ vrec,
+                                                         uint32_t* __restrict__ vbin, uint32_t* __restrict__ hist, float slack) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags || !sc.wmask) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t u0 = warp_id << 5; u0 < n; u0 += warps_total << 5) {
+        const uint32_t u = u0 + lane;
+        const bool active = u < n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) { x = ustart[3 * (size_t) u]; y = ustart[3 * (size_t) u + 1]; z = ustart[3 * (size_t) u + 2]; }
+        uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = lo;
+        if (active) { const uint32_t r = urec[u]; lo = __ldg(vl + 2 * (size_t) r); hi = __ldg(vl + 2 * (size_t) r + 1); }
+        uint32_t ncand = tile_union_lists(sc, lo, hi);
+        if (ncand == SDM_TLIST_NONE) {   // a creating voxel without a record: candidates from the cell masks of the balls' boxes
+            cell_union_box(grid, sc, active, x - slack, y - slack, z - slack, x + slack, y + slack, z + slack);
+            ncand = tile_candidates_from_mask(sc);
+        }
+        uint16_t* own = reinterpret_cast<uint16_t*>(vrec + 2 * (size_t) u);
+        // the lane's ball: every iterate within `slack` of the start point, plus the empirical_normal stencil around it
+        tile_refine(sc, ncand, active, x - slack * 0.57735027f, y - slack * 0.57735027f, z - slack * 0.57735027f, x + slack * 0.57735027f,
+                    y + slack * 0.57735027f, z + slack * 0.57735027f, 0.0021f, own, 0.0f, 0.0021f);
+        if (active) {
+            const uint4 a = vrec[2 * (size_t) u], b = vrec[2 * (size_t) u + 1];   // this thread's own stores
+            const uint32_t key = hash96(a.x ^ (b.x * 0x9E3779B1u), a.y ^ (b.y * 0x85EBCA77u), a.z ^ (a.w * 0xC2B2AE3Du) ^ (b.z * 0x27D4EB2Fu) ^ b.w) & (SDM_BINS - 1u);
+            vbin[u] = key;
+            atomicAdd(hist + key, 1u);
+        }
+    }
+}
+// exclusive scan of the SDM_BINS counters, in place: hist[b] becomes the first position of bin b (and then its cursor)
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* hist) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = SDM_BINS / 1024u, b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per; i++) sum += hist[b0 + i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint32_t i = 0; i < per; i++) { const uint32_t c = hist[b0 + i]; hist[b0 + i] = run; run += c; }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(DevState* st, uint32_t cap_uniq, const uint32_t* __restrict__ vbin, uint32_t* hist, uint32_t* __restrict__ perm) {
+    const uint32_t n = min(st->n_uniq, cap_uniq);
+    if (st->error_flags) return;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) perm[atomicAdd(hist + vbin[u], 1u)] = u;
+}
+
 // closest_surface_point per distinct mid-point (signed_distance.cu:227-240), bulk phase: one lane per vertex; lanes that
 // finish pull the next vertex (warp-level refill from a global ticket), so a warp's lanes stay busy although iteration
 // counts differ.  A vertex that is still running after SDM_NEWTON_BULK_ITERS iterations is handed, with its state, to
@@ -633,7 +738,8 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
                                                  float* __restrict__ upos, uint32_t cap_uniq, Straggler* __restrict__ stragglers,
                                                  uint32_t cap_stragglers, MaskGrid grid, uint32_t max_chunk,
                                                  const uint4* __restrict__ vl /* list records, or null: cell masks only */,
-                                                 const uint32_t* __restrict__ urec, uint32_t* __restrict__ uesc, float slack2) {
+                                                 const uint32_t* __restrict__ urec, uint32_t* __restrict__ uesc, float slack2,
+                                                 const uint32_t* __restrict__ perm /* binned order + per-vertex records in vl (urec unused), or null */) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
@@ -670,11 +776,11 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
             }
             const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
             if (!have && idx < chunk_end) {
-                uid = idx; it = 0; have = true;
-                gx = ustart[3 * (size_t) idx]; gy = ustart[3 * (size_t) idx + 1]; gz = ustart[3 * (size_t) idx + 2];
+                uid = perm ? perm[idx] : idx; it = 0; have = true;
+                gx = ustart[3 * (size_t) uid]; gy = ustart[3 * (size_t) uid + 1]; gz = ustart[3 * (size_t) uid + 2];
                 cyc.start(gx, gy, gz);
                 inr = true;
-                if (lists) rec = urec[idx];
+                if (lists) rec = perm ? uid : urec[uid];
             }
             chunk_next = min(chunk_next + (uint32_t) __popc(need), chunk_end);
         }
@@ -686,7 +792,8 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
         // its start point, which lies on the creating voxel: k_refine proved the records on the voxels inflated by that much),
         // else the cell masks at the lanes' current iterates.
         bool listed = false;
-        if (lists && __all_sync(0xffffffffu, !have || inr)) listed = tile_list_from_records(sc, have, vl, rec);
+        if (lists && __all_sync(0xffffffffu, !have || inr))
+            listed = perm ? tile_list_from_own_records(sc, have, vl, rec) : tile_list_from_records(sc, have, vl, rec, gx, gy, gz);
         if (!listed) { tile_mask_from_point(grid, sc, have, gx, gy, gz); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, have));
         if (have) {
@@ -830,7 +937,8 @@ __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* _
 __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
                                                         float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
                                                         uint32_t weld_max_entries, uint32_t* __restrict__ wref,
-                                                        const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, const uint32_t* __restrict__ uesc) {
+                                                        const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, const uint32_t* __restrict__ uesc,
+                                                        const uint32_t* __restrict__ perm) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t n = min(st->n_uniq, cap_uniq);
@@ -853,15 +961,16 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
         }
         const uint32_t u0 = g0 + 32u * gk;
         if (u0 >= n) { if (gk == 0) break; gk = group - 1; continue; }
-        const uint32_t u = u0 + lane;
-        const bool active = u < n;
+        const bool active = u0 + lane < n;
+        const uint32_t u = active ? (perm ? perm[u0 + lane] : u0 + lane) : 0u;
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
         if (weld_table && active) wref[u] = weld_insert_key(st, upos, u, weld_table, table_mask);
         bool listed = false;
         if (lists) {
             const bool esc = active && ((uesc[u >> 5] >> (u & 31u)) & 1u);
-            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, active, vl, active ? urec[u] : 0u);
+            if (!__any_sync(0xffffffffu, esc))
+                listed = perm ? tile_list_from_own_records(sc, active, vl, u) : tile_list_from_records(sc, active, vl, active ? urec[u] : 0u, x, y, z);
         }
         if (!listed) { tile_mask_from_point(grid, sc, active, x, y, z); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 12u * min(32u, n - u0);
@@ -921,7 +1030,7 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
         if (lists) {
             bool esc = false;
             if (t < T) esc = (((uesc[u[0] >> 5] >> (u[0] & 31u)) | (uesc[u[1] >> 5] >> (u[1] & 31u)) | (uesc[u[2] >> 5] >> (u[2] & 31u))) & 1u) != 0u;
-            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, t < T, vl, t < T ? tri_rec[t] : 0u);
+            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, t < T, vl, t < T ? tri_rec[t] : 0u, mx, my, mz);
         }
         if (!listed) { tile_mask_from_point(grid, sc, t < T, mx, my, mz); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 12u * min(32u, T - t0);
@@ -1245,6 +1354,24 @@ __global__ void __launch_bounds__(1024) k_scan_bits_1block(const uint32_t* __res
     uint32_t run = s_part[threadIdx.x] - sum;
     for (uint32_t w = w0; w < w1; w++) { word_prefix[w] = run; run += __popc(bits[w]); }
 }
+// the same with the number of BITS read from device memory
+__global__ void __launch_bounds__(1024) k_scan_bits_1block_dev(const uint32_t* __restrict__ bits, uint32_t* __restrict__ word_prefix, const uint32_t* nbits) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t nwords = *nbits / 32u + 2u;
+    const uint32_t per = (nwords + 1023u) / 1024u, w0 = threadIdx.x * per, w1 = min(w0 + per, nwords);
+    uint32_t sum = 0;
+    for (uint32_t w = w0; w < w1; w++) sum += __popc(bits[w]);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint32_t w = w0; w < w1; w++) { word_prefix[w] = run; run += __popc(bits[w]); }
+}
 // pass 3: (local index, global id of the owner) for every duplicate, grouped by shard; global offset of every shard
 __global__ void __launch_bounds__(256) k_res_pairs(const uint4* __restrict__ rows, uint32_t total, const uint4* __restrict__ table, const uint32_t* __restrict__ rref,
                                                    ShardOffsets so, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
@@ -1293,6 +1420,209 @@ __global__ void __launch_bounds__(256) k_fix_indices(ShardOffsets so, ShardTriOf
         const uint32_t c = so.voff[s] + idx[j];
         idx[j] = ((bitmap[c >> 5] >> (c & 31u)) & 1u) ? remap[c] : c - bit_rank(bitmap, prefix, c);
     }
+}
+
+// ---- peer exchange: the distributed weld driven from the device (one process per GPU, peer-mapped memory on rank 0) ------------
+// Rank 0 owns a control block, one slot of key rows per rank, the duplicate-pair lists and the output set the merged mesh is
+// assembled in; every other rank maps them (CUDA IPC) and reads / writes them with plain loads and stores over NVLink.  A step
+// never touches the host between its first and its last kernel:
+//   P0  every rank : its shard, welded locally; header {V, T, x range, errors} -> rank 0's control block; flag A
+//   P1  every rank : [all flags A] its welded vertices inside another shard's x range -> key rows in its slot on rank 0; flag B
+//   P2  rank 0     : [all flags B] owner per key (lowest shard), removal bitmap + prefix over the concatenated vertex lists,
+//                    per-shard global offsets and (local index, owner's global id) pairs; flag C
+//   P3  every rank : [flag C] drops its own duplicates, makes its indices global and STORES its rows at their final offsets -
+//                    straight into rank 0's output set over NVLink, or into its own second output set (host delivery: every
+//                    rank then copies its part over its own PCIe link); flag D
+//   P4  rank 0     : [all flags D] the merged mesh is complete (byte-identical to the single-GPU mesh).
+// Flags carry the step's epoch (monotonic), the payload of step e lives in slot e & 1, so a fast rank may run one step ahead.
+// Each flag is set by a one-thread kernel AFTER the kernels that wrote the payload (stream order) with a system-scope fence; the
+// waiters are one-block kernels that spin on the flags (ld.acquire.sys).  With fewer GPUs than ranks (tests) the phases are
+// issued one after the other with host synchronisation in between and no waiter is launched.
+#define SDM_PEER_MAX 32
+struct PeerHdr { uint32_t V, T, K, err; float min_x, max_x; uint32_t pad[2]; };
+struct PeerCtl {
+    uint32_t flagA[SDM_PEER_MAX], flagB[SDM_PEER_MAX], flagD[SDM_PEER_MAX];
+    uint32_t flagC, pad0[31];
+    PeerHdr hdr[2][SDM_PEER_MAX];
+    uint32_t voff[2][SDM_PEER_MAX + 1], toff[2][SDM_PEER_MAX + 1], goff[2][SDM_PEER_MAX + 1], poff[2][SDM_PEER_MAX + 1];
+    uint32_t dups[2][SDM_PEER_MAX], cursor[2][SDM_PEER_MAX];
+    uint32_t status[2], total_rows[2];
+};
+struct PeerLocal { uint32_t goff, toff, kept, T, status, total_V, total_T, pad; };   // what a rank's host reads after a step
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one block; thread i waits for flags[i] to reach `epoch`
+__global__ void k_peer_wait(const uint32_t* flags, uint32_t count, uint32_t epoch) {
+    if (threadIdx.x < count) {
+        while ((int32_t) (ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(200);
+    }
+}
+__global__ void k_peer_set_flag(uint32_t* flag, uint32_t epoch) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { __threadfence_system(); st_release_sys(flag, epoch); }
+}
+// P0: header of this rank's welded shard (scratch: k_shard_xrange's {min ordered x, max ordered x, non-finite count})
+__global__ void k_peer_publish_header(DevState* st, const uint32_t* __restrict__ scratch, PeerCtl* ctl, uint32_t rank, uint32_t parity) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    PeerHdr hd;
+    hd.V = st->n_verts_out; hd.T = st->n_tris_out; hd.K = 0;
+    hd.err = st->error_flags | (scratch[2] ? 0x100u : 0u) | (st->n_verts_out >= (1u << 24) ? 0x200u : 0u);   // 24-bit local indices in the key rows
+    hd.min_x = ord2f((int) scratch[0]); hd.max_x = ord2f((int) scratch[1]);
+    if (scratch[0] == 0x7fffffffu) { hd.min_x = 1.0f; hd.max_x = 0.0f; }   // no finite vertex
+    hd.pad[0] = hd.pad[1] = 0;
+    ctl->hdr[parity][rank] = hd;
+}
+// P1: key rows of the welded vertices that lie inside another shard's x range (equal keys are < 1.1e-5 apart; the ranges are
+// widened by 1e-4, or by four units of the key grid's float spacing where coordinates are large) -> this rank's slot on rank 0
+__global__ void __launch_bounds__(256) k_peer_rows(DevState* st, const float* __restrict__ out_pos, const PeerCtl* ctl, uint32_t rank, uint32_t world,
+                                                   uint32_t parity, uint4* __restrict__ slot_rows, uint32_t cap_rows, uint32_t* counter) {
+    __shared__ float s_lo[SDM_PEER_MAX], s_hi[SDM_PEER_MAX];
+    if (threadIdx.x < world) {
+        const PeerHdr hd = ctl->hdr[parity][threadIdx.x];
+        const float m = fmaxf(fabsf(hd.min_x), fabsf(hd.max_x));
+        const float wd = fmaxf(1e-4f, m * 4.8e-7f);
+        const bool use = threadIdx.x != rank && hd.min_x <= hd.max_x;
+        s_lo[threadIdx.x] = use ? hd.min_x - wd : 1.0f;
+        s_hi[threadIdx.x] = use ? hd.max_x + wd : 0.0f;
+    }
+    __syncthreads();
+    const uint32_t n = st->n_verts_out;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = out_pos[3 * (size_t) i];
+        bool cand = false;
+        for (uint32_t q = 0; q < world; q++) cand = cand || (x >= s_lo[q] && x <= s_hi[q]);
+        if (!cand) continue;
+        const uint32_t slot = atomicAdd(counter, 1u);
+        if (slot < cap_rows)
+            slot_rows[slot] = make_uint4(weld_key_component(x), weld_key_component(out_pos[3 * (size_t) i + 1]), weld_key_component(out_pos[3 * (size_t) i + 2]),
+                                         (rank << 24) | i);
+    }
+}
+__global__ void k_peer_publish_rows(const uint32_t* counter, PeerCtl* ctl, uint32_t rank, uint32_t parity, uint32_t cap_rows) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t k = *counter;
+    ctl->hdr[parity][rank].K = min(k, cap_rows);
+    if (k > cap_rows) ctl->hdr[parity][rank].err |= 0x400u;   // more boundary candidates than the slot holds
+}
+// P2 (rank 0), step 1: offsets of the concatenated vertex / triangle lists; any rank's error fails the step for everybody
+__global__ void k_peer_root_offsets(PeerCtl* ctl, uint32_t world, uint32_t parity, uint32_t cap_vertices, uint32_t cap_triangles) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t v = 0, t = 0, k = 0, err = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        const PeerHdr hd = ctl->hdr[parity][r];
+        ctl->voff[parity][r] = v; ctl->toff[parity][r] = t;
+        if ((uint64_t) v + hd.V > 0xFFFFFFFFull || (uint64_t) t + hd.T > 0xFFFFFFFFull) err |= 0x800u;
+        v += hd.V; t += hd.T; k += hd.K; err |= hd.err;
+        ctl->dups[parity][r] = 0; ctl->cursor[parity][r] = 0;
+    }
+    ctl->voff[parity][world] = v; ctl->toff[parity][world] = t;
+    if (v > cap_vertices || t > cap_triangles) err |= 0x800u;   // the merged mesh does not fit in rank 0's output set
+    ctl->status[parity] = err;
+    ctl->total_rows[parity] = k;
+}
+// rows live in per-rank slots of cap_rows entries: row g of the flattened space is rows[g] if (g % cap_rows) < K of rank g / cap_rows
+__device__ __forceinline__ bool peer_row(const PeerCtl* ctl, uint32_t parity, uint32_t cap_rows, uint32_t g) { return (g % cap_rows) < ctl->hdr[parity][g / cap_rows].K; }
+__global__ void __launch_bounds__(256) k_peer_res_insert(const PeerCtl* ctl, uint32_t world, uint32_t parity, uint32_t cap_rows, const uint4* __restrict__ rows, uint4* table,
+                                                         uint32_t table_mask, uint32_t* __restrict__ rref, uint32_t* status) {
+    if (*status) return;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < world * cap_rows; g += gridDim.x * blockDim.x) {
+        if (!peer_row(ctl, parity, cap_rows, g)) continue;
+        const uint4 r = rows[g];
+        bool won;
+        const uint32_t pos = hash_find_or_insert(table, table_mask, r.x, r.y, r.z, r.w, &won);
+        rref[g] = pos;
+        if (pos == 0xFFFFFFFFu) { atomicOr(status, 0x1000u); continue; }
+        if (!won) atomicMin(reinterpret_cast<uint32_t*>(table + pos) + 3, r.w);
+    }
+}
+// a row that is not its key's owner is a duplicate: bit in the removal bitmap (concatenated vertex space), count per shard
+__global__ void __launch_bounds__(256) k_peer_res_mark(PeerCtl* ctl, uint32_t world, uint32_t parity, uint32_t cap_rows, const uint4* __restrict__ rows, const uint4* __restrict__ table,
+                                                       const uint32_t* __restrict__ rref, uint32_t* __restrict__ bitmap) {
+    if (ctl->status[parity]) return;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < world * cap_rows; g += gridDim.x * blockDim.x) {
+        if (!peer_row(ctl, parity, cap_rows, g)) continue;
+        const uint32_t me = rows[g].w, pos = rref[g];
+        if (pos == 0xFFFFFFFFu || reinterpret_cast<const uint32_t*>(table + pos)[3] == me) continue;
+        const uint32_t s = me >> 24, c = ctl->voff[parity][s] + (me & 0xFFFFFFu);
+        atomicOr(bitmap + (c >> 5), 1u << (c & 31u));
+        atomicAdd(&ctl->dups[parity][s], 1u);
+    }
+}
+__global__ void k_peer_root_goff(PeerCtl* ctl, uint32_t world, uint32_t parity) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t g = 0, p = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        ctl->goff[parity][r] = g; ctl->poff[parity][r] = p;
+        g += ctl->hdr[parity][r].V - ctl->dups[parity][r]; p += ctl->dups[parity][r];
+    }
+    ctl->goff[parity][world] = g; ctl->poff[parity][world] = p;
+}
+// (local index, global id of the owner) for every duplicate, grouped by shard
+__global__ void __launch_bounds__(256) k_peer_res_pairs(PeerCtl* ctl, uint32_t world, uint32_t parity, uint32_t cap_rows, const uint4* __restrict__ rows, const uint4* __restrict__ table,
+                                                        const uint32_t* __restrict__ rref, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                                                        uint2* __restrict__ pairs) {
+    if (ctl->status[parity]) return;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < world * cap_rows; g += gridDim.x * blockDim.x) {
+        if (!peer_row(ctl, parity, cap_rows, g)) continue;
+        const uint32_t me = rows[g].w, pos = rref[g];
+        if (pos == 0xFFFFFFFFu) continue;
+        const uint32_t owner = reinterpret_cast<const uint32_t*>(table + pos)[3];
+        if (owner == me) continue;
+        const uint32_t s = me >> 24, oc = ctl->voff[parity][owner >> 24] + (owner & 0xFFFFFFu);
+        const uint32_t slot = ctl->poff[parity][s] + atomicAdd(&ctl->cursor[parity][s], 1u);
+        pairs[slot] = make_uint2(me & 0xFFFFFFu, oc - bit_rank(bitmap, prefix, oc));   // the owner itself is never removed
+    }
+}
+// P3: this rank's duplicates into its own removal bitmap + owner map (local vertex space)
+__global__ void __launch_bounds__(256) k_peer_apply_mark(const PeerCtl* ctl, uint32_t rank, uint32_t parity, const uint2* __restrict__ pairs, uint32_t* __restrict__ bitmap,
+                                                         uint32_t* __restrict__ remap, PeerLocal* local) {
+    const uint32_t p0 = ctl->poff[parity][rank], np = ctl->poff[parity][rank + 1] - p0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        local->goff = ctl->goff[parity][rank]; local->toff = ctl->toff[parity][rank]; local->kept = ctl->hdr[parity][rank].V - np;
+        local->T = ctl->hdr[parity][rank].T; local->status = ctl->status[parity];
+        local->total_V = 0; local->total_T = 0;
+    }
+    if (ctl->status[parity]) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[p0 + i];
+        atomicOr(bitmap + (pr.x >> 5), 1u << (pr.x & 31u));
+        remap[pr.x] = pr.y;
+    }
+}
+// kept vertices to their global rows (dst: rank 0's output set over NVLink, or this rank's own second set)
+__global__ void __launch_bounds__(256) k_peer_apply_vertices(const PeerCtl* ctl, uint32_t rank, uint32_t parity, const uint32_t* __restrict__ bitmap,
+                                                             const uint32_t* __restrict__ prefix, const float* __restrict__ in_pos, const float* __restrict__ in_nrm,
+                                                             float* __restrict__ dst_pos, float* __restrict__ dst_nrm, uint32_t dst_is_global) {
+    if (ctl->status[parity]) return;
+    const uint32_t V = ctl->hdr[parity][rank].V;
+    const uint32_t base = dst_is_global ? ctl->goff[parity][rank] : 0u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < V; c += gridDim.x * blockDim.x) {
+        if ((bitmap[c >> 5] >> (c & 31u)) & 1u) continue;
+        const size_t o = (size_t) base + c - bit_rank(bitmap, prefix, c);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { dst_pos[3 * o + k] = in_pos[3 * (size_t) c + k]; dst_nrm[3 * o + k] = in_nrm[3 * (size_t) c + k]; }
+    }
+}
+// every index becomes global: own kept vertex -> goff + its rank among the kept ones, duplicate -> its owner's global id
+__global__ void __launch_bounds__(256) k_peer_apply_indices(const PeerCtl* ctl, uint32_t rank, uint32_t parity, const uint32_t* __restrict__ bitmap,
+                                                            const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ remap, const uint32_t* __restrict__ in_idx,
+                                                            uint32_t* __restrict__ dst_idx, uint32_t dst_is_global) {
+    if (ctl->status[parity]) return;
+    const uint32_t n3 = 3u * ctl->hdr[parity][rank].T, goff = ctl->goff[parity][rank];
+    const size_t base = dst_is_global ? 3 * (size_t) ctl->toff[parity][rank] : 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n3; j += gridDim.x * blockDim.x) {
+        const uint32_t c = in_idx[j];
+        dst_idx[base + j] = ((bitmap[c >> 5] >> (c & 31u)) & 1u) ? remap[c] : goff + c - bit_rank(bitmap, prefix, c);
+    }
+}
+// totals for the host of rank 0 (and of every rank, for bookkeeping)
+__global__ void k_peer_totals(const PeerCtl* ctl, uint32_t world, uint32_t parity, PeerLocal* local) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    local->total_V = ctl->goff[parity][world]; local->total_T = ctl->toff[parity][world]; local->status = ctl->status[parity];
 }
 
 // ---- test / probe kernels -------------------------------------------------------------------------

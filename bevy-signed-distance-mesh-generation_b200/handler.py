@@ -78,6 +78,16 @@ class _ShardBuffers(ctypes.Structure):
                 ("capacity_vertices", ctypes.c_uint32), ("capacity_triangles", ctypes.c_uint32)]
 
 
+class _PeerExport(ctypes.Structure):
+    _fields_ = [("handle", (ctypes.c_ubyte * 64) * 4), ("block_bytes", ctypes.c_uint64), ("cap_vertices", ctypes.c_uint32),
+                ("cap_triangles", ctypes.c_uint32), ("cap_rows", ctypes.c_uint32), ("world", ctypes.c_uint32)]
+
+
+class _PeerResult(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("status", "total_vertices", "total_triangles", "vertex_offset", "triangle_offset", "vertices",
+                                               "triangles")] + [("gpu_ms", ctypes.c_float)]
+
+
 assert ctypes.sizeof(_VoxelField) == 32 and _VoxelField.voxels.offset == 16 and _VoxelField.voxel_count.offset == 24
 
 # every symbol include/sdfmesh.h declares (tests/test_abi.py checks the library exports each one)
@@ -89,7 +99,8 @@ ABI_SYMBOLS = [
     "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
     "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_fixup",
     "sdm_shard_welded_buffers", "sdm_shard_reserve_welded",
-    "sdm_mesh_save_obj", "sdm_hash_bytes",
+    "sdm_mesh_save_obj", "sdm_hash_bytes", "sdm_reserve", "sdm_peer_root_export", "sdm_peer_attach", "sdm_peer_step", "sdm_peer_finish",
+    "sdm_peer_download_async",
     "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
 
@@ -402,6 +413,41 @@ class CudaHandler:
     def save_obj(self, m, path) -> None:
         """sdm_mesh_save_obj of a device-resident mesh (`remesh(..., download=False)`)."""
         self._check(self._lib.sdm_mesh_save_obj(self._h, ctypes.byref(m), str(path).encode()))
+
+    # -- peer exchange (include/sdfmesh.h): the distributed weld driven from the device -------------------------------
+    def reserve(self, voxel_capacity: int) -> None:
+        self._check(self._lib.sdm_reserve(self._h, ctypes.c_uint32(voxel_capacity)))
+
+    def peer_root_export(self, world: int, cap_rows: int) -> bytes:
+        e = _PeerExport()
+        self._check(self._lib.sdm_peer_root_export(self._h, ctypes.c_uint32(world), ctypes.c_uint32(cap_rows), ctypes.byref(e)))
+        return bytes(e)
+
+    def peer_attach(self, export: bytes, rank: int, world: int, same_process_root: "CudaHandler | None" = None) -> None:
+        e = _PeerExport.from_buffer_copy(export)
+        root = same_process_root._h if same_process_root is not None else None
+        self._check(self._lib.sdm_peer_attach(self._h, ctypes.byref(e), ctypes.c_uint32(rank), ctypes.c_uint32(world), root))
+
+    def peer_step(self, bb_size, init_factor, levels, split_level, epoch, deliver=0, phase_mask=31, spin=True) -> None:
+        p = _params(bb_size, init_factor, levels)
+        self._check(self._lib.sdm_peer_step(self._h, ctypes.byref(p), ctypes.c_uint32(split_level), ctypes.c_uint32(epoch), ctypes.c_int(deliver),
+                                            ctypes.c_uint32(phase_mask), ctypes.c_int(1 if spin else 0)))
+
+    def peer_finish(self):
+        """-> (result dict, SdmMesh view): rank 0 with deliver = 0 gets the merged mesh, deliver = 1 gives every rank its own rows."""
+        r, m = _PeerResult(), _Mesh()
+        self._check(self._lib.sdm_peer_finish(self._h, ctypes.byref(r), ctypes.byref(m)))
+        return {n: getattr(r, n) for n, _ in _PeerResult._fields_}, m
+
+    def peer_download_async(self, result: dict, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:
+        r = _PeerResult(**result)
+        self._check(self._lib.sdm_peer_download_async(self._h, ctypes.byref(r), ctypes.c_void_p(positions_ptr), ctypes.c_void_p(normals_ptr),
+                                                      ctypes.c_void_p(indices_ptr)))
+
+    def sync(self) -> None:
+        """Waits for everything enqueued on the handle's stream (used between the phases of an emulated multi-rank step)."""
+        n = ctypes.c_uint32(0)
+        self._check(self._lib.sdm_field_count(self._h, ctypes.byref(n), None))
 
     def download_into(self, m, positions_ptr: int, normals_ptr: int, indices_ptr: int) -> None:
         """sdm_mesh_download into caller-provided (e.g. pinned) host memory."""

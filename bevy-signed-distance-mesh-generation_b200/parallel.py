@@ -106,6 +106,135 @@ def _view(torch, ptr, nelem, typestr, device):
     return torch.as_tensor(_DevView(ptr, nelem, typestr), device=device)
 
 
+def emulated_peer_step(handlers, bb_size, init_factor, levels, split_level, epoch, deliver=0):
+    """The peer exchange with the ranks emulated by several handles of ONE process on one GPU (tests): the phases are issued one
+    after the other, with a synchronisation in between instead of the device-side flags (kernels that wait for each other must not
+    share a GPU).  handlers[0] is rank 0.  -> [(result, mesh view)] per rank."""
+    for phase in (1, 2, 4, 8, 16):
+        for h in handlers:
+            h.peer_step(bb_size, init_factor, levels, split_level, epoch, deliver, phase, spin=False)
+        for h in handlers:
+            h.sync()
+    return [h.peer_finish() for h in handlers]
+
+
+def peer_capacities(total_vertices: int, total_triangles: int, world: int):
+    """(voxel capacity of rank 0, key rows per rank) for a merged mesh of the given size: rank 0's second output set must hold the whole
+    mesh (2 vertices / 3 triangles per voxel of capacity), with a quarter of head room; a rank's interface candidates are a fraction
+    of its vertices."""
+    cap_vox = int(max(total_vertices / 2.0, total_triangles / 3.0) * 1.25) + 4096
+    cap_rows = max(1 << 16, int(total_vertices / max(world, 1) / 2))
+    return cap_vox, cap_rows
+
+
+class PeerRemesher:
+    """step() = one full remesh on `world` GPUs (one process each) through the device-driven peer exchange (include/sdfmesh.h):
+    no host round trip, no NCCL on the data path - torch.distributed only carries the set-up (counts, the IPC handles).
+    deliver = 0: the merged mesh is assembled in rank 0's HBM over NVLink; deliver = 1: every rank keeps its rows and copies them
+    over its own PCIe link into a host buffer shared by the ranks (`shared_host`)."""
+
+    def __init__(self, handler, bb_size, init_factor, levels, rank, world, dist, split_level=None):
+        import torch
+
+        self.h, self.bb, self.init, self.levels = handler, bb_size, init_factor, levels
+        self.rank, self.world, self.dist = rank, world, dist
+        self.split_level = choose_split_level(init_factor, levels, world) if split_level is None else split_level
+        self.epoch = 0
+        self.last_gpu_ms = 0.0
+        self.mesh = None
+        self.last = None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # sizes, through the host-driven calls (once)
+        h = self.h
+        h.shard_remesh(bb_size, init_factor, levels, self.split_level, rank, world)
+        w = h.shard_local_weld()
+        mine = torch.tensor([w["vertices"], w["triangles"]], dtype=torch.int64, device=dev)
+        allc = torch.empty((world, 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        totals = allc.sum(dim=0).cpu().tolist()
+        self.cap_vox, self.cap_rows = peer_capacities(int(totals[0]), int(totals[1]), world)
+        if rank == 0:
+            h.reserve(self.cap_vox)
+        blob = [h.peer_root_export(world, self.cap_rows) if rank == 0 else None]
+        dist.broadcast_object_list(blob, src=0)
+        h.peer_attach(blob[0], rank, world)
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.shared = None
+
+    def step(self, deliver=0):
+        self.epoch += 1
+        self.h.peer_step(self.bb, self.init, self.levels, self.split_level, self.epoch, deliver, 31, True)
+        res, m = self.h.peer_finish()
+        self.last, self.mesh = res, (m if (deliver == 0 and self.rank == 0) else None)
+        self.last_gpu_ms = res["gpu_ms"]
+        return {"triangles": int(res["total_triangles"]), "vertices": int(res["total_vertices"])}
+
+    # -- end-to-end: scene from the host every step, every rank's rows into ONE host buffer over its own PCIe link ------------
+    def _shared_host(self, total_vertices, total_triangles):
+        """A host buffer shared by the ranks (POSIX shared memory, page-locked in every process): positions | normals | indices."""
+        import torch
+        from multiprocessing import shared_memory
+
+        nv, nt = int(total_vertices * 1.25) + 1024, int(total_triangles * 1.25) + 1024
+        size = nv * 24 + nt * 12
+        name = [None]
+        if self.rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=size)
+            name[0] = shm.name
+        self.dist.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        import ctypes
+
+        base = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        rc = torch.cuda.cudart().cudaHostRegister(base, size, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        self.shared = dict(shm=shm, base=base, size=size, pos=base, nrm=base + nv * 12, idx=base + nv * 24, nv=nv, nt=nt)
+        self.dist.barrier()
+        return self.shared
+
+    def e2e(self, scene, steps, warmup, barrier):
+        h = self.h
+        scene = np.ascontiguousarray(scene)
+        if self.shared is None:
+            r = self.step(deliver=1)
+            self._shared_host(r["vertices"], r["triangles"])
+        sh = self.shared
+        d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(warmup + steps):
+            if i == warmup:
+                h.download_wait()
+                barrier()
+                t0 = time.perf_counter()
+            h.set_scene(scene)                 # host -> device: the scene table (the path's only input), on every rank
+            r = self.step(deliver=1)
+            if r["vertices"] > sh["nv"] or r["triangles"] > sh["nt"]:
+                raise RuntimeError("shared host buffer too small")
+            h.peer_download_async(self.last, sh["pos"], sh["nrm"], sh["idx"])   # device -> host: this rank's rows, over its own link
+            d2h = self.last["vertices"] * 24 + self.last["triangles"] * 12
+        h.download_wait()
+        barrier()
+        return {"elapsed": time.perf_counter() - t0, "h2d": int(scene.nbytes), "d2h": d2h}
+
+    def close(self):
+        if self.shared is not None:
+            import torch
+
+            torch.cuda.cudart().cudaHostUnregister(self.shared["base"])
+            shm = self.shared["shm"]
+            self.shared = None
+            try:
+                shm.close()
+                if self.rank == 0:
+                    shm.unlink()
+            except Exception:
+                pass
+
+
 class ShardedRemesher:
     """step() = one full remesh on `world` GPUs; on rank 0 the welded mesh is left in HBM."""
 

@@ -240,6 +240,38 @@ int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total_
                       uint32_t* out_removed /* [shard_count] */);
 int sdm_shard_fixup(SdmHandle* h, const uint32_t* triangle_counts /* [shard_count of the last sdm_shard_resolve] */, SdmMesh* out_mesh);
 
+/* ---- peer exchange: the distributed weld without the host (one process per GPU on one node) ---------------------------------
+ * The calls above route every count through the host.  Here rank 0 exports a control block, per-rank key-row slots and its second
+ * output set (CUDA IPC); the other ranks map them, and one step runs from the first kernel to the last with device-side flags
+ * only (csrc/sdm_kernels.cuh, "peer exchange"): local weld -> x ranges -> interface key rows to rank 0 -> rank 0 resolves owners and
+ * global offsets -> every rank drops its own duplicates, makes its indices global and STORES its rows at their final offsets,
+ * either straight into rank 0's output set over NVLink (deliver = 0) or into its own second output set, from where it copies its part
+ * over its own PCIe link into a host buffer shared by the ranks (deliver = 1, sdm_peer_download_async).  The result is byte-identical
+ * to the single-GPU mesh.  Capacities are fixed at export time (sdm_reserve first); a step that does not fit fails on all ranks. */
+typedef struct SdmPeerExport {
+    unsigned char handle[4][64];     /* cudaIpcMemHandle_t of: control block, positions, normals, indices of rank 0's output set */
+    uint64_t block_bytes;
+    uint32_t cap_vertices, cap_triangles, cap_rows, world;
+} SdmPeerExport;
+typedef struct SdmPeerResult {
+    uint32_t status;                 /* 0 = ok; otherwise the OR of the ranks' error bits (the step produced nothing) */
+    uint32_t total_vertices, total_triangles;   /* the merged mesh */
+    uint32_t vertex_offset, triangle_offset;    /* where this rank's rows start in it */
+    uint32_t vertices, triangles;               /* this rank's rows (duplicates owned by lower ranks removed) */
+    float gpu_ms;                               /* CUDA-event time of the step on this rank's stream */
+} SdmPeerResult;
+int sdm_reserve(SdmHandle* h, uint32_t voxel_capacity);   /* grow the handle's buffers now (2 vertices / 3 triangles per voxel of capacity) */
+int sdm_peer_root_export(SdmHandle* h, uint32_t world, uint32_t cap_rows_per_rank, SdmPeerExport* out);            /* rank 0 */
+/* every rank (rank 0 too).  same_process_root != NULL: ranks emulated by several handles of one process (tests): rank 0's pointers are
+ * used directly, and the caller must issue the phases of a step one by one (phase_mask) with a synchronisation in between. */
+int sdm_peer_attach(SdmHandle* h, const SdmPeerExport* root, uint32_t rank, uint32_t world, SdmHandle* same_process_root);
+/* phase_mask: bit p = enqueue phase p (0..4); spin != 0: each phase first waits on the device for the flags it depends on
+ * (one rank per GPU only).  epoch: 1, 2, 3, ... the same on all ranks. */
+int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, uint32_t epoch, int deliver, uint32_t phase_mask, int spin);
+int sdm_peer_finish(SdmHandle* h, SdmPeerResult* out, SdmMesh* out_mesh /* rank 0 with deliver = 0: the merged mesh; else this rank's rows */);
+/* deliver = 1: this rank's rows into the shared host arrays at its offsets (asynchronous; sdm_mesh_download_wait) */
+int sdm_peer_download_async(SdmHandle* h, const SdmPeerResult* r, float* host_positions, float* host_normals, uint32_t* host_indices);
+
 /* ---- counters for the bench ------------------------------------------------------------------------ */
 typedef struct SdmStats {
     uint64_t kernel_launches;      /* kernels launched by this handle since creation */

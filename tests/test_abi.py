@@ -88,7 +88,8 @@ def test_header_is_plain_c_and_layouts_match_the_ctypes_mirrors(tmp_path):
     import subprocess
 
     structs = {"SdmPoint": H._Point, "SdmVoxelField": H._VoxelField, "SdmParams": H._Params, "SdmMesh": H._Mesh, "SdmStats": H._Stats,
-               "SdmShardInfo": H._ShardInfo, "SdmShardBuffers": H._ShardBuffers, "SdmShardWeld": H._ShardWeld}
+               "SdmShardInfo": H._ShardInfo, "SdmShardBuffers": H._ShardBuffers, "SdmShardWeld": H._ShardWeld,
+               "SdmPeerExport": H._PeerExport, "SdmPeerResult": H._PeerResult}
     src = tmp_path / "layout.c"
     body = "\n".join(f'    printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text('#include <stdio.h>\n#include "sdfmesh.h"\nint main(void) {\n' + body +

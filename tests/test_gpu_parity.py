@@ -212,3 +212,37 @@ def test_fullsize_matches_reference_goldens(handler, oracle_mod, case, init, lev
     assert h(mesh.indices) == want["fnv_indices"], "index topology differs"
     assert h(mesh.positions) == want["fnv_positions"], "vertex positions differ"
     assert h(mesh.normals) == want["fnv_normals"], "vertex normals differ"
+
+
+@pytest.mark.parametrize("switch", ["SDM_NO_BINS", "SDM_NO_LISTS", "SDM_NO_LATTICE", "SDM_SLACK=0.25"])
+def test_fallback_paths_give_the_same_mesh(handler, switch, monkeypatch):
+    """The fast paths (inherited primitive lists, vertices binned by record, 64-bit lattice vertex keys) each have a general path
+    behind them (cell masks, list order, float-bit keys) that also serves whatever the fast path cannot take; a small slack
+    sends many Newton iterates through the hand-over to the tail kernel.  All of them must produce the same bytes."""
+    scene = scenes.many_primitives(256)
+    handler.set_scene(scene)
+    want = handler.remesh(5.0, 32, 3)
+    name, _, value = switch.partition("=")
+    monkeypatch.setenv(name, value or "1")
+    h = bsdmg_b200.CudaHandler(0, scene)   # the switches are read when a handle is created
+    try:
+        got = h.remesh(5.0, 32, 3)
+        st = h.stats()
+    finally:
+        h.close()
+    assert np.array_equal(got.indices, want.indices)
+    assert np.array_equal(bits(got.positions), bits(want.positions)) and np.array_equal(bits(got.normals), bits(want.normals))
+    if switch.startswith("SDM_SLACK"):
+        assert st["stragglers"] > 0     # the hand-over really happened
+
+
+def test_non_dyadic_grid_falls_back_to_float_keys(handler, oracle_mod):
+    """INIT 24 over a domain of 5: 5/24 is not a dyadic fraction, voxel coordinates are rounded, the lattice check of the fast vertex
+    keys fails on the device (ERR_LATTICE) and the mesh stage is repeated with the generic keys - same mesh as the oracle."""
+    scene = scenes.many_primitives(64)
+    handler.set_scene(scene)
+    want = oracle_mod.Oracle(scene).remesh(5.0, 24, 2)
+    got = handler.remesh(5.0, 24, 2)
+    assert np.array_equal(got.indices, want["indices"]) and np.array_equal(bits(got.positions), bits(want["positions"]))
+    got = handler.remesh(5.0, 24, 2)            # second call: the handle remembers, no retry
+    assert np.array_equal(got.indices, want["indices"]) and np.array_equal(bits(got.normals), bits(want["normals"]))

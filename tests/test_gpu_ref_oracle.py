@@ -6,6 +6,8 @@ travels to the GPU box as a binary):
 2. the functor-template restatement of the two kernels reproduces the unmodified kernels byte for byte;
 3. Mandelbulb: the product equals the reference's device code (same libdevice transcendentals) bit for bit.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -102,11 +104,16 @@ def test_table_functor_on_gpu_equals_host(refgpu, oracle_mod):
     assert np.array_equal(bits(refgpu.mesh_raw(3, vox, vs)), bits(o.mesh_raw(vox, vs)[0]))
 
 
-@pytest.mark.parametrize("t,init,levels", [(None, 64, 1), (None, 32, 2), (None, 64, 2), (0.5, 64, 2), (3.0, 64, 2)])
+_SLOW = pytest.mark.skipif(not os.environ.get("SDM_SLOW_TESTS"), reason="~5 min each on a B200: the reference kernel re-runs a 10 000-iteration "
+                           "projection of the same never-converging vertex for every triangle corner that uses it (set SDM_SLOW_TESTS=1)")
+
+
+@pytest.mark.parametrize("t,init,levels", [(None, 64, 1), (0.5, 64, 2), (1.0, 32, 2), pytest.param(None, 32, 2, marks=_SLOW),
+                                           pytest.param(None, 64, 2, marks=_SLOW), pytest.param(3.0, 64, 2, marks=_SLOW)])
 def test_many1024_remesh_matches_reference_kernels(refgpu, handler, oracle_mod, t, init, levels):
-    """The 1024-primitive scene (static and two animated frames): every level's active list, the raw 5-slot triangle soup
+    """The 1024-primitive scene (static and animated frames): every level's active list, the raw 5-slot triangle soup
     and the welded mesh of the CUDA path (culled fold, W = 32 mask words, 64^3 mask grid) against the reference's kernels
-    evaluating all 1024 primitives at every point."""
+    evaluating all 1024 primitives at every point.  (All six cases passed on the B200 in round 2; three are opt-in for time.)"""
     table = scenes.many_primitives(1024, t=t)
     handler.set_scene(table)
     lists, vs = _ref_descent(refgpu, table, 5.0, init, levels, oracle_mod)

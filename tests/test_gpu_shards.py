@@ -103,3 +103,49 @@ def test_distributed_weld_equals_single(scene_name, init, levels, split, G):
     finally:
         for h in hs:
             h.close()
+
+
+@pytest.mark.parametrize("scene_name,init,levels,split,G", [("sd_obj", 32, 3, 1, 2), ("sd_obj", 32, 3, 2, 3), ("many64", 32, 2, 1, 4),
+                                                            ("many256", 32, 3, 1, 4), ("sphere_box", 32, 2, 1, 2), ("sd_obj", 32, 2, 2, 7),
+                                                            ("sd_obj", 32, 2, 0, 1)])
+@pytest.mark.parametrize("deliver", [0, 1])
+def test_peer_exchange_equals_single(scene_name, init, levels, split, G, deliver):
+    """The device-driven exchange (include/sdfmesh.h, "peer exchange") with the ranks emulated by G handles on one GPU (phases
+    issued one after the other: no kernel waits for another one here).  deliver = 0: the merged mesh in rank 0's second output
+    set; deliver = 1: every rank's own rows, assembled on the host at the offsets the step reports.  Same bytes as the
+    single-handle mesh either way, over two consecutive steps (the payload slots alternate with the epoch)."""
+    scene = scenes.many_primitives(int(scene_name[4:])) if scene_name.startswith("many") else scenes.SCENES[scene_name]()
+    hs = [bsdmg_b200.CudaHandler(0, scene) for _ in range(G)]
+    try:
+        single = hs[0].remesh(5.0, init, levels)
+        cap_vox, cap_rows = parallel.peer_capacities(single.vertex_count, single.triangle_count, G)
+        hs[0].reserve(max(cap_vox, init ** 3))
+        blob = hs[0].peer_root_export(G, cap_rows)
+        for r, h in enumerate(hs):
+            h.peer_attach(blob, r, G, same_process_root=hs[0])
+        for epoch in (1, 2):
+            out = parallel.emulated_peer_step(hs, 5.0, init, levels, split, epoch, deliver)
+            res0 = out[0][0]
+            assert res0["status"] == 0
+            assert (res0["total_vertices"], res0["total_triangles"]) == (single.vertex_count, single.triangle_count)
+            if deliver == 0:
+                merged = hs[0]._download(out[0][1])
+            else:
+                pos = np.empty((single.vertex_count, 3), np.float32); nrm = np.empty_like(pos)
+                idx = np.empty((single.triangle_count, 3), np.uint32)
+                v_end = t_end = 0
+                for h, (res, m) in zip(hs, out):
+                    part = h._download(m)
+                    assert part.vertex_count == res["vertices"] and part.triangle_count == res["triangles"]
+                    assert res["vertex_offset"] == v_end and res["triangle_offset"] == t_end      # the ranks' rows tile the mesh in rank order
+                    pos[v_end:v_end + res["vertices"]] = part.positions; nrm[v_end:v_end + res["vertices"]] = part.normals
+                    idx[t_end:t_end + res["triangles"]] = part.indices
+                    v_end += res["vertices"]; t_end += res["triangles"]
+                assert (v_end, t_end) == (single.vertex_count, single.triangle_count)
+                merged = bsdmg_b200.Mesh(pos, nrm, idx)
+            assert np.array_equal(merged.indices, single.indices)
+            assert np.array_equal(bits(merged.positions), bits(single.positions))
+            assert np.array_equal(bits(merged.normals), bits(single.normals))
+    finally:
+        for h in hs:
+            h.close()
