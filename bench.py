@@ -256,7 +256,7 @@ def main():
     config = {"workload": args.workload, "description": desc, "scene": scene_name, "primitives": int(scene.shape[0]),
               "bb_size": bb, "init_factor": init, "levels": levels, "resolution": res,
               "l2": "every step clears >0.3 GB of tables / bitmaps and rewrites all intermediates (working set > 126 MB L2); no separate flush",
-              "parallelism": (f"x-slab shards of the level-{_par.choose_split_level(init, levels, max(world, args.gpus))} active list over {max(world, args.gpus)} GPU(s), "
+              "parallelism": (f"x-slab shards of the level-{_par.choose_split_level(init, levels, max(world, args.gpus), _par.scene_is_culled(scene))} active list over {max(world, args.gpus)} GPU(s), "
                               "welded where they are made, interface keys resolved and shards assembled on rank 0 (NCCL)") if max(world, args.gpus) > 1 else "1 GPU"}
 
     if args.impl == "reference":
@@ -290,14 +290,14 @@ def main():
     exchange = "single"
     if world > 1 and args.exchange == "peer":
         try:   # device-driven exchange over peer-mapped memory (CUDA IPC); the host-driven NCCL exchange remains as the fallback
-            runner = parallel.PeerRemesher(h, bb, init, levels, rank, world, dist)
+            runner = parallel.PeerRemesher(h, bb, init, levels, rank, world, dist, culled=parallel.scene_is_culled(scene))
             exchange = "peer (device-side flags, stores over NVLink into rank 0 / per-rank PCIe for e2e)"
         except Exception as exc:   # noqa: BLE001 - any set-up failure (IPC not permitted, ...) must not lose the measurement
             print(f"[rank {rank}] peer exchange unavailable ({exc}); using the NCCL exchange", file=sys.stderr, flush=True)
-            runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist)
+            runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist, culled=parallel.scene_is_culled(scene))
             exchange = "nccl (host-driven)"
     else:
-        runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist)
+        runner = parallel.ShardedRemesher(h, bb, init, levels, rank, world, dist, culled=parallel.scene_is_culled(scene))
         if world > 1:
             exchange = "nccl (host-driven)"
 

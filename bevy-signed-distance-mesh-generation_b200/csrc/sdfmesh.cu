@@ -242,8 +242,6 @@ struct SdmHandle {
     float list_delta = 0.0f;           // inflation of the boxes the current records are proven on (= slack of the mesh stage)
     float delta_override = 0.0f;       // > 0: sdm_remesh knows the final voxel size and uses one inflation for all levels
     DevBuf<uint32_t> urec, tri_rec;    // per vertex / per raw triangle: its list record
-    DevBuf<uint4> vrec;                // per vertex: its OWN record (k_vertex_lists)
-    DevBuf<uint32_t> vbin, perm, hist; // binning of the vertices by record: bin per vertex, vertices in bin order, bin counters
     DevBuf<uint32_t> uesc;             // bitmap: vertices that ended outside their record's region
     EdgeLattice lattice {};            // integer lattice of the current field (k_edges' fast keys); enabled = 0: generic keys
     bool lattice_ok = true;            // cleared when a mesh stage reported ERR_LATTICE for the current field
@@ -293,12 +291,10 @@ struct SdmHandle {
     bool mesh_valid = false;
 
     // persistent grid sizes
-    int g_vlists = 0;
     int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0, g_edges = 0;
-    uint32_t bin_chunk = 64;            // ... when the vertices are walked in bin order (SDM_BIN_CHUNK)
     uint32_t proj_chunk = 256;          // vertex chunk per warp in k_project (SDM_PROJ_CHUNK overrides)
     float slack_factor = 1.0f;         // inflation of the list regions in units of the child voxel size (SDM_SLACK overrides)
-    bool use_lists = true, use_lattice = true, use_bins = true;   // SDM_NO_LISTS / SDM_NO_LATTICE / SDM_NO_BINS: developer switches for A/B measurements
+    bool use_lists = true, use_lattice = true;   // SDM_NO_LISTS / SDM_NO_LATTICE: developer switches for A/B measurements
 
     SdmStats stats {};
 
@@ -370,7 +366,6 @@ int configure_kernels(SdmHandle* h) {
         { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_cases, 256, &h->g_classify },
         { (const void*) k_project, 128, &h->g_project }, { (const void*) k_vertex_normals, 128, &h->g_normals },
         { (const void*) k_orient, 128, &h->g_orient },   { (const void*) k_project_tail, 128, &h->g_tail },
-        { (const void*) k_vertex_lists, 128, &h->g_vlists },
     };
     for (const K& k : ks) {
         const size_t smem = smem_for(h, k.threads);
@@ -441,10 +436,6 @@ int reserve_all(SdmHandle* h, uint32_t cap_vox, uint32_t cap_tris, uint32_t cap_
     for (int i = 0; i < 2; i++) { CK(h->vl[i].reserve((size_t) cap_vox * 2)); CK(h->vparent[i].reserve(cap_vox)); }
     CK(h->tri_rec.reserve(cap_tris));
     CK(h->urec.reserve(cap_uniq));
-    CK(h->vrec.reserve((size_t) cap_uniq * 2));
-    CK(h->vbin.reserve(cap_uniq));
-    CK(h->perm.reserve(cap_uniq));
-    CK(h->hist.reserve(SDM_BINS));
     CK(h->uesc.reserve((size_t) cap_uniq / 32 + 32));
     CK(h->m27.reserve(cap_vox));
     CK(h->tri_off.reserve(cap_vox));
@@ -577,6 +568,26 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
 }
 
 // clears sized on the device from n_uniq / n_tris_raw (which must already be in DevState)
+// this rank's contiguous part of the current list -> the other ping-pong buffer.  At level 0 of a culled scene the parts are
+// balanced by the cells' surface flags (no level needs to be refined redundantly on every rank); otherwise equal parts.
+int enqueue_take_shard(SdmHandle* h, uint32_t shard_index, uint32_t shard_count) {
+    const bool vp = h->lists_level == h->level;   // the shard's voxels keep their record indices
+    const uint32_t* bounds = nullptr;
+    if (h->level == 0 && h->grid.enabled && h->grid.maybe && h->grid.G == h->field_init && shard_count > 1) {
+        k_shard_bounds_by_flags<<<1, 1024, 0, h->stream>>>(h->grid.maybe, h->grid.G * h->grid.G * h->grid.G, shard_index, shard_count, h->shard_range.p + 4);
+        bounds = h->shard_range.p + 4;
+        h->stats.kernel_launches++;
+    }
+    k_take_shard<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, shard_index, shard_count, h->shard_range.p,
+                                                     vp ? h->vparent[h->vp_cur].p : nullptr, vp ? h->vparent[h->vp_cur ^ 1].p : nullptr, bounds);
+    k_set_level_count<<<1, 1, 0, h->stream>>>(h->state.p, h->level, h->shard_range.p);
+    mark(h, "k_take_shard");
+    h->stats.kernel_launches += 2;
+    h->cur ^= 1;
+    if (vp) h->vp_cur ^= 1;
+    return SDM_OK;
+}
+
 int enqueue_weld_clears(SdmHandle* h, bool clear_first_slot) {
     k_clear_weld_state<<<h->g_light, 256, 0, h->stream>>>(h->state.p, h->first_slot.p, h->first_bits.p, h->table2.p, h->table_entries,
                                                           h->cap_uniq, clear_first_slot ? 1 : 0, clear_first_slot ? h->uesc.p : nullptr);
@@ -623,24 +634,10 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     int rc = enqueue_weld_clears(h, true);
     if (rc) return rc;
     mark(h, "k_clear_weld_state");
-    // per-vertex records + binning: the per-vertex kernels then walk the vertices in bin order with warp-uniform lists
-    const bool bins = lists && h->use_bins;
-    const uint4* vlv = bins ? h->vrec.p : vl;
-    const uint32_t* perm = bins ? h->perm.p : nullptr;
-    if (bins) {
-        NvtxRange nv(h, "mesh: vertex records + binning");
-        CK(dev_fill(s, h->hist.p, 0, (size_t) SDM_BINS * 4));
-        k_vertex_lists<<<h->g_vlists, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->cap_uniq, h->grid, vl, h->urec.p, h->vrec.p, h->vbin.p, h->hist.p, h->list_delta);
-        mark(h, "k_vertex_lists");
-        k_bin_scan<<<1, 1024, 0, s>>>(h->hist.p);
-        k_bin_scatter<<<h->g_light, 256, 0, s>>>(h->state.p, h->cap_uniq, h->vbin.p, h->hist.p, h->perm.p);
-        mark(h, "k_bin_scan+scatter");
-        h->stats.kernel_launches += 4;
-    }
     {
         NvtxRange nv(h, "mesh: project");
         k_project<<<h->g_project, 128, smem128, s>>>(h->scene.p, h->state.p, h->ustart.p, h->upos.p, h->cap_uniq, h->stragglers.p, h->cap_stragglers, h->grid,
-                                                     bins ? h->bin_chunk : h->proj_chunk, vlv, h->urec.p, h->uesc.p, slack2, perm);
+                                                     h->proj_chunk, vl, h->urec.p, h->uesc.p, slack2);
         mark(h, "k_project");
         k_project_tail<<<h->g_tail, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->stragglers.p, h->cap_stragglers, h->grid, h->ustart.p,
                                                        vl ? h->uesc.p : nullptr, slack2);
@@ -649,7 +646,7 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     {
         NvtxRange nv(h, "mesh: vertex normals + weld keys");
         k_vertex_normals<<<h->g_normals, 128, smem128, s>>>(h->scene.p, h->state.p, h->upos.p, h->unrm.p, h->cap_uniq, h->grid,
-                                                            fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p, vlv, h->urec.p, h->uesc.p, perm);
+                                                            fuse_weld_keys ? h->table2.p : nullptr, h->table_entries, h->wref.p, vl, h->urec.p, h->uesc.p);
         mark(h, "k_vertex_normals");
     }
     {
@@ -822,7 +819,7 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         memset(h->host_state, 0, sizeof(DevState));
         if (cudaMallocHost(&h->host_range, 16) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMallocHost"); break; }
         memset(h->host_range, 0, 16);
-        if (h->shard_range.reserve(4) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc range"); break; }
+        if (h->shard_range.reserve(8) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc range"); break; }
         if (h->state.reserve(1) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, "cudaMalloc state"); break; }
         dev_fill(h->stream, h->state.p, 0, sizeof(DevState));
         cudaMemcpyToSymbolAsync(c_mc_packed, SDM_MC_PACKED_INIT, sizeof(SDM_MC_PACKED_INIT), 0, cudaMemcpyHostToDevice, h->stream);
@@ -830,11 +827,9 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         cudaMemcpyToSymbolAsync(c_mc_ntri, SDM_MC_NTRI_INIT, sizeof(SDM_MC_NTRI_INIT), 0, cudaMemcpyHostToDevice, h->stream);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(SDM_ERR_CUDA, std::string("init: ") + cudaGetErrorString(cudaGetLastError())); break; }
         if (const char* e = getenv("SDM_SLACK")) { const float v = (float) atof(e); if (v > 0.0f && v <= 8.0f) h->slack_factor = v; }
-        if (const char* e = getenv("SDM_BIN_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->bin_chunk = (uint32_t) v & ~31u; }
         if (const char* e = getenv("SDM_PROJ_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->proj_chunk = (uint32_t) v & ~31u; }
         h->use_lists = getenv("SDM_NO_LISTS") == nullptr;
         h->use_lattice = getenv("SDM_NO_LATTICE") == nullptr;
-        h->use_bins = getenv("SDM_NO_BINS") == nullptr;
         SdmPrimitive def[2];
         sdm_scene_default(def, 2);
         rc = sdm_set_scene(h, def, 2);
@@ -859,7 +854,7 @@ void sdm_destroy(SdmHandle* h) {
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
     h->entry_uid.release(); h->vidx.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release();
     for (int i = 0; i < 2; i++) { h->vl[i].release(); h->vparent[i].release(); }
-    h->urec.release(); h->tri_rec.release(); h->uesc.release(); h->vrec.release(); h->vbin.release(); h->perm.release(); h->hist.release(); h->stragglers.release(); h->state.release();
+    h->urec.release(); h->tri_rec.release(); h->uesc.release(); h->stragglers.release(); h->state.release();
     if (h->host_state) cudaFreeHost(h->host_state);
     if (h->host_range) cudaFreeHost(h->host_range);
     if (h->host_scratch) cudaFreeHost(h->host_scratch);
@@ -1370,16 +1365,8 @@ int sdm_shard_remesh(SdmHandle* h, const SdmParams* params, uint32_t split_level
         h->delta_override = h->slack_factor * ldexpf(p.bb_size / (float) p.init_factor, -(int) p.levels);
         for (uint32_t l = 0; l < split_level && !rc; l++) rc = enqueue_refine(h);   // redundantly on every rank: the coarse levels are tiny
         if (rc) { h->delta_override = 0.0f; return rc; }
-        {
-            const bool vp = h->lists_level == h->level;   // the shard's voxels keep their record indices
-            k_take_shard<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, shard_index, shard_count,
-                                                             h->shard_range.p, vp ? h->vparent[h->vp_cur].p : nullptr, vp ? h->vparent[h->vp_cur ^ 1].p : nullptr);
-            k_set_level_count<<<1, 1, 0, h->stream>>>(h->state.p, h->level, h->shard_range.p);
-            mark(h, "k_take_shard");
-            h->stats.kernel_launches += 2;
-            h->cur ^= 1;
-            if (vp) h->vp_cur ^= 1;
-        }
+        rc = enqueue_take_shard(h, shard_index, shard_count);
+        if (rc) { h->delta_override = 0.0f; return rc; }
         for (uint32_t l = split_level; l < p.levels && !rc; l++) rc = enqueue_refine(h, l + 1 == p.levels);
         h->delta_override = 0.0f;
         if (rc) return rc;
@@ -1767,16 +1754,8 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         h->delta_override = h->slack_factor * ldexpf(p.bb_size / (float) p.init_factor, -(int) p.levels);
         for (uint32_t l = 0; l < split_level && !rc; l++) rc = enqueue_refine(h);
         if (rc) { h->delta_override = 0.0f; return rc; }
-        {
-            const bool vp = h->lists_level == h->level;
-            k_take_shard<<<h->g_light, 256, 0, s>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, rank, world, h->shard_range.p,
-                                                     vp ? h->vparent[h->vp_cur].p : nullptr, vp ? h->vparent[h->vp_cur ^ 1].p : nullptr);
-            k_set_level_count<<<1, 1, 0, s>>>(h->state.p, h->level, h->shard_range.p);
-            mark(h, "k_take_shard");
-            h->stats.kernel_launches += 2;
-            h->cur ^= 1;
-            if (vp) h->vp_cur ^= 1;
-        }
+        rc = enqueue_take_shard(h, rank, world);
+        if (rc) { h->delta_override = 0.0f; return rc; }
         for (uint32_t l = split_level; l < p.levels && !rc; l++) rc = enqueue_refine(h, l + 1 == p.levels);
         h->delta_override = 0.0f;
         if (rc) return rc;

@@ -422,13 +422,14 @@ __device__ __forceinline__ bool lattice_axis(float b, float s, float o, float h,
     return n >= 0 && n < (1 << 21) - 2 && __float_as_uint(o + fn * h) == __float_as_uint(b) &&
            __float_as_uint(o + (fn + 2.0f) * h) == __float_as_uint(hi) && __float_as_uint(o + (fn + 1.0f) * h) == __float_as_uint(mid);
 }
-// lattice coordinates (half-voxel units, relative to the voxel's base index) of the mid-point of edge e
+// lattice coordinates (half-voxel units, relative to the voxel's base index) of the mid-point of edge e: 0, 1 or 2 per axis, two bits
+// per edge packed into one word per axis (edge e joins the corners of MC_EDGE_TABLE[e]; corner c: +x iff c%4 in {1,2}, +y iff c%4 >= 2,
+// +z iff c >= 4; tests/test_tables.py checks the packed words against the tables)
+#define SDM_EDGE_DX 0x281919u
+#define SDM_EDGE_DY 0xa06464u
+#define SDM_EDGE_DZ 0x55aa00u
 __device__ __forceinline__ void edge_lattice_offset(int e, int& dx, int& dy, int& dz) {
-    int c0, c1;
-    mc_edge_corners(e, c0, c1);
-    const int x0 = ((c0 & 3) == 1 || (c0 & 3) == 2) ? 2 : 0, y0 = ((c0 & 3) >= 2) ? 2 : 0, z0 = (c0 >= 4) ? 2 : 0;
-    const int x1 = ((c1 & 3) == 1 || (c1 & 3) == 2) ? 2 : 0, y1 = ((c1 & 3) >= 2) ? 2 : 0, z1 = (c1 >= 4) ? 2 : 0;
-    dx = (x0 + x1) >> 1; dy = (y0 + y1) >> 1; dz = (z0 + z1) >> 1;
+    dx = (int) ((SDM_EDGE_DX >> (2 * e)) & 3u); dy = (int) ((SDM_EDGE_DY >> (2 * e)) & 3u); dz = (int) ((SDM_EDGE_DZ >> (2 * e)) & 3u);
 }
 __device__ __forceinline__ unsigned long long lattice_key(int ux, int uy, int uz) {
     return 1ull + ((unsigned long long) (uint32_t) ux | ((unsigned long long) (uint32_t) uy << 21) | ((unsigned long long) (uint32_t) uz << 42));
@@ -512,7 +513,13 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
                         unsigned long long cur = s_key[p];
                         if (cur == 0ull) {
                             cur = atomicCAS(&s_key[p], 0ull, key);
-                            if (cur == 0ull) { own_mask |= 1u << e; ref = p; break; }
+                            if (cur == 0ull) {   // this thread owns the key in the tile: it will do the global find-or-insert
+                                own_mask |= 1u << e; ref = p;
+                                const uint32_t g0 = hash_key64(key) & table_mask;
+                                s_gpos[p] = g0;
+                                prefetch_l2(table8 + g0);
+                                break;
+                            }
                         }
                         if (cur == key) { ref = p; break; }
                         p = (p + 1u) & (SDM_EDGE_SLOTS - 1u);
@@ -526,18 +533,13 @@ __global__ void __launch_bounds__(256) k_edges(const float* __restrict__ vox, De
                     }
                     s_eref[e * 256 + threadIdx.x] = ref;
                 }
-                // phase 2a: start the global table lines of the keys this thread owns on their way
-                for (uint32_t m = own_mask; m; m &= m - 1u) {
-                    const int e = __ffs((int) m) - 1;
-                    prefetch_l2(table8 + (hash_key64(s_key[s_eref[e * 256 + threadIdx.x]]) & table_mask));
-                }
-                // phase 2b: one global find-or-insert per distinct key of the tile
+                // phase 2: one global find-or-insert per distinct key of the tile (its table line is already on its way)
                 for (uint32_t m = own_mask; m; m &= m - 1u) {
                     const int e = __ffs((int) m) - 1;
                     const uint32_t p = s_eref[e * 256 + threadIdx.x];
                     const unsigned long long key = s_key[p];
                     bool w;
-                    const uint32_t gp = hash64_probe_from(table8, table_mask, hash_key64(key) & table_mask, key, &w);
+                    const uint32_t gp = hash64_probe_from(table8, table_mask, s_gpos[p], key, &w);
                     if (gp == 0xFFFFFFFFu) { full = true; w = false; }
                     if (w) won_mask |= 1u << e;
                     s_gpos[p] = gp & 0x7FFFFFFFu;
@@ -656,71 +658,6 @@ __global__ void __launch_bounds__(256) k_clear_weld_state(DevState* st, uint32_t
     if (tid == 0) { st->n_tris_out = 0; st->n_verts_out = 0; st->ticket[TK_SCAN_FIRST] = 0; st->ticket[TK_SCAN_TRI] = 0; st->ticket[TK_PROJECT] = 0; st->n_stragglers = 0; st->ticket[TK_TAIL] = 0; st->weld_dups = 0; }
 }
 
-// ---- per-vertex lists and binning (culled scenes) ------------------------------------------------------------------------------
-// A warp folds the UNION of its lanes' lists, so a lane pays for primitives only its neighbours need: with vertices taken in list
-// order the union is about twice a lane's own need-list.  Here every vertex gets its own record - the exact per-lane test on the
-// ball (start point, slack + stencil reach), candidates from the records of the voxels that created the tile's vertices - and
-// the vertices are then BINNED by record: k_project / k_vertex_normals walk them in bin order, so the lanes of a warp mostly hold
-// the same record and the union is what each lane needs anyway.  Order does not matter to the result: every vertex is projected
-// from its own start point, and output order is decided by the weld.  (Counting sort by a 16-bit hash of the record: histogram
-// here, k_bin_scan, k_bin_scatter; equal records share a bin, the order inside a bin is whatever the atomics give.)
-#define SDM_BINS 65536u
-__global__ void __launch_bounds__(128, 8) k_vertex_lists(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ ustart, uint32_t cap_uniq,
-                                                         MaskGrid grid, const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, uint4* __restrict__ vrec,
-                                                         uint32_t* __restrict__ vbin, uint32_t* __restrict__ hist, float slack) {
-    extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene_masked(scene, smem, grid);
-    const uint32_t n = min(st->n_uniq, cap_uniq);
-    if (st->error_flags || !sc.wmask) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    for (uint32_t u0 = warp_id << 5; u0 < n; u0 += warps_total << 5) {
-        const uint32_t u = u0 + lane;
-        const bool active = u < n;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (active) { x = ustart[3 * (size_t) u]; y = ustart[3 * (size_t) u + 1]; z = ustart[3 * (size_t) u + 2]; }
-        uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = lo;
-        if (active) { const uint32_t r = urec[u]; lo = __ldg(vl + 2 * (size_t) r); hi = __ldg(vl + 2 * (size_t) r + 1); }
-        uint32_t ncand = tile_union_lists(sc, lo, hi);
-        if (ncand == SDM_TLIST_NONE) {   // a creating voxel without a record: candidates from the cell masks of the balls' boxes
-            cell_union_box(grid, sc, active, x - slack, y - slack, z - slack, x + slack, y + slack, z + slack);
-            ncand = tile_candidates_from_mask(sc);
-        }
-        uint16_t* own = reinterpret_cast<uint16_t*>(vrec + 2 * (size_t) u);
-        // the lane's ball: every iterate within `slack` of the start point, plus the empirical_normal stencil around it
-        tile_refine(sc, ncand, active, x - slack * 0.57735027f, y - slack * 0.57735027f, z - slack * 0.57735027f, x + slack * 0.57735027f,
-                    y + slack * 0.57735027f, z + slack * 0.57735027f, 0.0021f, own, 0.0f, 0.0021f);
-        if (active) {
-            const uint4 a = vrec[2 * (size_t) u], b = vrec[2 * (size_t) u + 1];   // this thread's own stores
-            const uint32_t key = hash96(a.x ^ (b.x * 0x9E3779B1u), a.y ^ (b.y * 0x85EBCA77u), a.z ^ (a.w * 0xC2B2AE3Du) ^ (b.z * 0x27D4EB2Fu) ^ b.w) & (SDM_BINS - 1u);
-            vbin[u] = key;
-            atomicAdd(hist + key, 1u);
-        }
-    }
-}
-// exclusive scan of the SDM_BINS counters, in place: hist[b] becomes the first position of bin b (and then its cursor)
-__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* hist) {
-    __shared__ uint32_t s_part[1024];
-    const uint32_t per = SDM_BINS / 1024u, b0 = threadIdx.x * per;
-    uint32_t sum = 0;
-    for (uint32_t i = 0; i < per; i++) sum += hist[b0 + i];
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    for (uint32_t o = 1; o < 1024u; o <<= 1) {
-        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = s_part[threadIdx.x] - sum;
-    for (uint32_t i = 0; i < per; i++) { const uint32_t c = hist[b0 + i]; hist[b0 + i] = run; run += c; }
-}
-__global__ void __launch_bounds__(256) k_bin_scatter(DevState* st, uint32_t cap_uniq, const uint32_t* __restrict__ vbin, uint32_t* hist, uint32_t* __restrict__ perm) {
-    const uint32_t n = min(st->n_uniq, cap_uniq);
-    if (st->error_flags) return;
-    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) perm[atomicAdd(hist + vbin[u], 1u)] = u;
-}
-
 // closest_surface_point per distinct mid-point (signed_distance.cu:227-240), bulk phase: one lane per vertex; lanes that
 // finish pull the next vertex (warp-level refill from a global ticket), so a warp's lanes stay busy although iteration
 // counts differ.  A vertex that is still running after SDM_NEWTON_BULK_ITERS iterations is handed, with its state, to
@@ -738,8 +675,7 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
                                                  float* __restrict__ upos, uint32_t cap_uniq, Straggler* __restrict__ stragglers,
                                                  uint32_t cap_stragglers, MaskGrid grid, uint32_t max_chunk,
                                                  const uint4* __restrict__ vl /* list records, or null: cell masks only */,
-                                                 const uint32_t* __restrict__ urec, uint32_t* __restrict__ uesc, float slack2,
-                                                 const uint32_t* __restrict__ perm /* binned order + per-vertex records in vl (urec unused), or null */) {
+                                                 const uint32_t* __restrict__ urec, uint32_t* __restrict__ uesc, float slack2) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
@@ -768,19 +704,26 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
             if (!need) break;
             if (chunk_next >= chunk_end) {
                 if (drained) break;
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&st->ticket[TK_PROJECT], CHUNK);
+                // guided hand-out: chunks shrink as the work runs out (half of an even share of what is left, at least one tile),
+                // so that the warps finish together whatever the vertex count per warp is (shards of a multi-GPU run are small)
+                uint32_t base = 0, len = 0;
+                if (lane == 0) {
+                    const uint32_t taken = min(*(volatile uint32_t*) &st->ticket[TK_PROJECT], n);
+                    len = min(CHUNK, max(32u, (((n - taken) / (warps_in_grid * 2u)) + 31u) & ~31u));
+                    base = atomicAdd(&st->ticket[TK_PROJECT], len);
+                }
                 base = __shfl_sync(0xffffffffu, base, 0);
+                len = __shfl_sync(0xffffffffu, len, 0);
                 if (base >= n) { drained = true; break; }
-                chunk_next = base; chunk_end = min(base + CHUNK, n);
+                chunk_next = base; chunk_end = min(base + len, n);
             }
             const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
             if (!have && idx < chunk_end) {
-                uid = perm ? perm[idx] : idx; it = 0; have = true;
+                uid = idx; it = 0; have = true;
                 gx = ustart[3 * (size_t) uid]; gy = ustart[3 * (size_t) uid + 1]; gz = ustart[3 * (size_t) uid + 2];
                 cyc.start(gx, gy, gz);
                 inr = true;
-                if (lists) rec = perm ? uid : urec[uid];
+                if (lists) rec = urec[uid];
             }
             chunk_next = min(chunk_next + (uint32_t) __popc(need), chunk_end);
         }
@@ -792,8 +735,7 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
         // its start point, which lies on the creating voxel: k_refine proved the records on the voxels inflated by that much),
         // else the cell masks at the lanes' current iterates.
         bool listed = false;
-        if (lists && __all_sync(0xffffffffu, !have || inr))
-            listed = perm ? tile_list_from_own_records(sc, have, vl, rec) : tile_list_from_records(sc, have, vl, rec, gx, gy, gz);
+        if (lists && __all_sync(0xffffffffu, !have || inr)) listed = tile_list_from_records(sc, have, vl, rec, gx, gy, gz);
         if (!listed) { tile_mask_from_point(grid, sc, have, gx, gy, gz); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, have));
         if (have) {
@@ -937,8 +879,7 @@ __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* _
 __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
                                                         float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
                                                         uint32_t weld_max_entries, uint32_t* __restrict__ wref,
-                                                        const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, const uint32_t* __restrict__ uesc,
-                                                        const uint32_t* __restrict__ perm) {
+                                                        const uint4* __restrict__ vl, const uint32_t* __restrict__ urec, const uint32_t* __restrict__ uesc) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t n = min(st->n_uniq, cap_uniq);
@@ -952,25 +893,29 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
     unsigned long long work = 0;
     // tiles are handed out dynamically, a few at a time (every warp should still get >= ~4 hand-outs): their cost varies with the list
     // lengths, and a static split left a tail
-    const uint32_t group = tile_group((n + 31u) >> 5, warps_total);
+    uint32_t group = tile_group((n + 31u) >> 5, warps_total);
     for (uint32_t g0 = 0, gk = group;; gk++) {
         if (gk == group) {
-            if (lane == 0) g0 = atomicAdd(&st->ticket[TK_NORMALS], 32u * group);
+            if (lane == 0) {   // guided: the groups shrink as the work runs out
+                const uint32_t taken = min(*(volatile uint32_t*) &st->ticket[TK_NORMALS], n);
+                group = max(1u, min(8u, (n - taken) / (warps_total * 64u)));
+                g0 = atomicAdd(&st->ticket[TK_NORMALS], 32u * group);
+            }
             g0 = __shfl_sync(0xffffffffu, g0, 0);
+            group = __shfl_sync(0xffffffffu, group, 0);
             gk = 0;
         }
         const uint32_t u0 = g0 + 32u * gk;
         if (u0 >= n) { if (gk == 0) break; gk = group - 1; continue; }
-        const bool active = u0 + lane < n;
-        const uint32_t u = active ? (perm ? perm[u0 + lane] : u0 + lane) : 0u;
+        const uint32_t u = u0 + lane;
+        const bool active = u < n;
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
         if (weld_table && active) wref[u] = weld_insert_key(st, upos, u, weld_table, table_mask);
         bool listed = false;
         if (lists) {
             const bool esc = active && ((uesc[u >> 5] >> (u & 31u)) & 1u);
-            if (!__any_sync(0xffffffffu, esc))
-                listed = perm ? tile_list_from_own_records(sc, active, vl, u) : tile_list_from_records(sc, active, vl, active ? urec[u] : 0u, x, y, z);
+            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, active, vl, active ? urec[u] : 0u, x, y, z);
         }
         if (!listed) { tile_mask_from_point(grid, sc, active, x, y, z); fallbacks += lists ? 1u : 0u; }
         work += (unsigned long long) tile_prims(sc) * 12u * min(32u, n - u0);
@@ -1001,11 +946,16 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long work = 0;
-    const uint32_t group = tile_group((T + 31u) >> 5, warps_total);
-    for (uint32_t g0 = 0, gk = group;; gk++) {   // dynamic hand-out, see k_vertex_normals
+    uint32_t group = tile_group((T + 31u) >> 5, warps_total);
+    for (uint32_t g0 = 0, gk = group;; gk++) {   // dynamic, guided hand-out, see k_vertex_normals
         if (gk == group) {
-            if (lane == 0) g0 = atomicAdd(&st->ticket[TK_ORIENT], 32u * group);
+            if (lane == 0) {
+                const uint32_t taken = min(*(volatile uint32_t*) &st->ticket[TK_ORIENT], T);
+                group = max(1u, min(8u, (T - taken) / (warps_total * 64u)));
+                g0 = atomicAdd(&st->ticket[TK_ORIENT], 32u * group);
+            }
             g0 = __shfl_sync(0xffffffffu, g0, 0);
+            group = __shfl_sync(0xffffffffu, group, 0);
             gk = 0;
         }
         const uint32_t t0 = g0 + 32u * gk;
@@ -1218,11 +1168,52 @@ __global__ void __launch_bounds__(256) k_soup(DevState* st, int level, const uin
 // Restrict the list of `level` to the contiguous part [n*shard/count, n*(shard+1)/count) (64-bit arithmetic),
 // copied to the front of the other ping-pong buffer.  Children keep their parent's order (compute_mesh_generation.cu:51)
 // and level 0 is x-major (src/cuda/mod.rs:110-119), so a contiguous part of the list is an x-slab at every level.
+// Shard bounds in the DENSE level-0 list weighted by the cells' "may contain the surface" flags (k_build_masks): every shard gets the
+// same number of flagged cells, so that no level has to be refined redundantly to find a balanced split.  bounds[0..1] = [lo, hi);
+// the same arithmetic on every rank, so the shards tile the list.
+__global__ void __launch_bounds__(1024) k_shard_bounds_by_flags(const uint8_t* __restrict__ flags, uint32_t n, uint32_t shard, uint32_t count, uint32_t* bounds) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (n + 1023u) / 1024u, i0 = min(threadIdx.x * per, n), i1 = min(i0 + per, n);
+    uint32_t sum = 0;
+    if ((per & 15u) == 0u && i1 - i0 == per && (reinterpret_cast<uintptr_t>(flags) & 15u) == 0u) {   // 16 flags per load (they are 0 / 1 bytes)
+        const uint4* f4 = reinterpret_cast<const uint4*>(flags + i0);
+        for (uint32_t q = 0; q < per / 16u; q++) {
+            const uint4 w = __ldg(f4 + q);
+            sum += __popc(w.x & 0x01010101u) + __popc(w.y & 0x01010101u) + __popc(w.z & 0x01010101u) + __popc(w.w & 0x01010101u);
+        }
+    } else {
+        for (uint32_t i = i0; i < i1; i++) sum += flags[i] ? 1u : 0u;
+    }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const uint32_t total = s_part[1023], before = s_part[threadIdx.x] - sum;
+    if (threadIdx.x == 0) { bounds[0] = 0; bounds[1] = n; }   // shard 0 starts at 0, the last one ends at n; also the answer when nothing is flagged
+    __syncthreads();
+    // boundary b (b = shard, shard + 1) = index of flagged cell number total * b / count; whoever holds it writes it
+    for (uint32_t b = 0; b < 2u; b++) {
+        const uint32_t which = shard + b;
+        if (which == 0u || which == count || total == 0u) continue;
+        const uint32_t target = (uint32_t) ((uint64_t) total * which / count);
+        if (target >= before && target < before + sum) {
+            uint32_t seen = before;
+            for (uint32_t i = i0; i < i1; i++)
+                if (flags[i]) { if (seen == target) { bounds[b] = i; break; } seen++; }
+        }
+    }
+}
 __global__ void __launch_bounds__(256) k_take_shard(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
                                                     uint32_t shard, uint32_t count, uint32_t* __restrict__ range_out,
-                                                    const uint32_t* __restrict__ vp_in, uint32_t* __restrict__ vp_out) {
+                                                    const uint32_t* __restrict__ vp_in, uint32_t* __restrict__ vp_out,
+                                                    const uint32_t* __restrict__ bounds /* precomputed [lo, hi), or null: equal parts */) {
     const uint32_t n = st->level_count[level];
-    const uint32_t lo = (uint32_t) ((uint64_t) n * shard / count), hi = (uint32_t) ((uint64_t) n * (shard + 1) / count);
+    const uint32_t lo = bounds ? min(bounds[0], n) : (uint32_t) ((uint64_t) n * shard / count);
+    const uint32_t hi = bounds ? min(max(bounds[1], lo), n) : (uint32_t) ((uint64_t) n * (shard + 1) / count);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * (hi - lo); i += gridDim.x * blockDim.x) out_vox[i] = in_vox[3 * (size_t) lo + i];
     if (vp_in)   // list record (= parent) indices travel with the voxels
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < hi - lo; i += gridDim.x * blockDim.x) vp_out[i] = vp_in[lo + i];

@@ -84,11 +84,20 @@ def concat_welded_shards(shards, candidate_masks=None):
     return positions, normals, indices
 
 
-def choose_split_level(init_factor: int, levels: int, world: int) -> int:
-    """Coarse levels are refined redundantly on every rank; the split happens once the list is long enough that an
-    equal-count split is also a balanced split of the final work (>= ~64 voxels per rank per SM is plenty), and
-    never later than level 2 so that the redundant part stays negligible."""
-    if world <= 1:
+def scene_is_culled(scene) -> bool:
+    """The library's rule for using per-cell primitive masks (csrc/sdfmesh.cu, sdm_set_scene): more than 24 compiled primitives
+    (a box skeleton counts 12) and no Mandelbulb."""
+    from .scenes import BOX_SKELETON, MANDELBULB
+
+    kinds = [int(k) for k in scene["kind"]]
+    return MANDELBULB not in kinds and sum(12 if k == BOX_SKELETON else 1 for k in kinds) > 24
+
+
+def choose_split_level(init_factor: int, levels: int, world: int, culled: bool = False) -> int:
+    """Culled scenes split the dense level-0 list itself, balanced by the mask cells' surface flags (k_shard_bounds_by_flags):
+    nothing is refined redundantly.  Otherwise coarse levels are refined on every rank and the split happens once the list is
+    long enough that an equal-count split is also a balanced split of the final work, never later than level 2."""
+    if world <= 1 or culled:
         return 0
     return min(levels, 1 if init_factor >= 64 else 2)
 
@@ -133,12 +142,12 @@ class PeerRemesher:
     deliver = 0: the merged mesh is assembled in rank 0's HBM over NVLink; deliver = 1: every rank keeps its rows and copies them
     over its own PCIe link into a host buffer shared by the ranks (`shared_host`)."""
 
-    def __init__(self, handler, bb_size, init_factor, levels, rank, world, dist, split_level=None):
+    def __init__(self, handler, bb_size, init_factor, levels, rank, world, dist, split_level=None, culled=False):
         import torch
 
         self.h, self.bb, self.init, self.levels = handler, bb_size, init_factor, levels
         self.rank, self.world, self.dist = rank, world, dist
-        self.split_level = choose_split_level(init_factor, levels, world) if split_level is None else split_level
+        self.split_level = choose_split_level(init_factor, levels, world, culled) if split_level is None else split_level
         self.epoch = 0
         self.last_gpu_ms = 0.0
         self.mesh = None
@@ -238,10 +247,10 @@ class PeerRemesher:
 class ShardedRemesher:
     """step() = one full remesh on `world` GPUs; on rank 0 the welded mesh is left in HBM."""
 
-    def __init__(self, handler, bb_size, init_factor, levels, rank=0, world=1, dist=None):
+    def __init__(self, handler, bb_size, init_factor, levels, rank=0, world=1, dist=None, culled=False):
         self.h, self.bb, self.init, self.levels = handler, bb_size, init_factor, levels
         self.rank, self.world, self.dist = rank, world, dist
-        self.split_level = choose_split_level(init_factor, levels, world)
+        self.split_level = choose_split_level(init_factor, levels, world, culled)
         self.last_gpu_ms = 0.0
         self.mesh = None
         self._pinned = None

@@ -214,10 +214,10 @@ def test_fullsize_matches_reference_goldens(handler, oracle_mod, case, init, lev
     assert h(mesh.normals) == want["fnv_normals"], "vertex normals differ"
 
 
-@pytest.mark.parametrize("switch", ["SDM_NO_BINS", "SDM_NO_LISTS", "SDM_NO_LATTICE", "SDM_SLACK=0.25"])
+@pytest.mark.parametrize("switch", ["SDM_NO_LISTS", "SDM_NO_LATTICE", "SDM_SLACK=0.25"])
 def test_fallback_paths_give_the_same_mesh(handler, switch, monkeypatch):
-    """The fast paths (inherited primitive lists, vertices binned by record, 64-bit lattice vertex keys) each have a general path
-    behind them (cell masks, list order, float-bit keys) that also serves whatever the fast path cannot take; a small slack
+    """The fast paths (inherited primitive lists, 64-bit lattice vertex keys) each have a general path
+    behind them (cell masks, float-bit keys) that also serves whatever the fast path cannot take; a small slack
     sends many Newton iterates through the hand-over to the tail kernel.  All of them must produce the same bytes."""
     scene = scenes.many_primitives(256)
     handler.set_scene(scene)
@@ -246,3 +246,32 @@ def test_non_dyadic_grid_falls_back_to_float_keys(handler, oracle_mod):
     assert np.array_equal(got.indices, want["indices"]) and np.array_equal(bits(got.positions), bits(want["positions"]))
     got = handler.remesh(5.0, 24, 2)            # second call: the handle remembers, no retry
     assert np.array_equal(got.indices, want["indices"]) and np.array_equal(bits(got.normals), bits(want["normals"]))
+
+
+def test_generated_mesh_obj_of_the_headless_run(handler, oracle_mod, tmp_path):
+    """f1: the reference's headless run (src/main.rs:20-34) meshes the level-0 field of sd_obj (2 088 triangles / 1 038 vertices) and
+    its next Advance writes generated_mesh.obj (src/renderer/mod.rs:204).  sdm_mesh_save_obj of the device-resident mesh, parsed
+    back, must give the oracle's mesh: positions and normals bit for bit (shortest round-trip decimals), faces a/1/a b/1/b c/1/c."""
+    handler.set_scene(scenes.sd_obj())
+    m = handler.remesh(5.0, 32, 0, download=False)
+    path = tmp_path / "generated_mesh.obj"
+    handler.save_obj(m, path)
+    want = oracle_mod.Oracle(scenes.sd_obj()).remesh(5.0, 32, 0)
+    assert want["indices"].shape[0] == 2088 and want["positions"].shape[0] == 1038
+    v, vn, f, other = [], [], [], []
+    for line in path.read_text().splitlines():
+        tag, *rest = line.split()
+        if tag == "v":
+            v.append([np.float32(x) for x in rest])
+        elif tag == "vn":
+            vn.append([np.float32(x) for x in rest])
+        elif tag == "f":
+            tri = [tuple(int(q) for q in c.split("/")) for c in rest]
+            assert all(t == 1 and p == n for p, t, n in tri)
+            f.append([p - 1 for p, _, _ in tri])
+        else:
+            other.append(line)
+    assert other == ["vt 0 0", "o default", "g default"]
+    assert np.array_equal(bits(np.array(v, np.float32)), bits(want["positions"]))
+    assert np.array_equal(bits(np.array(vn, np.float32)), bits(want["normals"]))
+    assert np.array_equal(np.array(f, np.uint32), want["indices"])

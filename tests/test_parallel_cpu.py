@@ -30,6 +30,9 @@ def test_split_level_choice():
     assert parallel.choose_split_level(32, 5, 8) == 2
     assert parallel.choose_split_level(128, 4, 8) == 1
     assert parallel.choose_split_level(64, 0, 4) == 0
+    assert parallel.choose_split_level(64, 4, 8, culled=True) == 0     # culled scenes: level-0 split by the cells' surface flags
+    assert parallel.scene_is_culled(scenes.many_primitives(1024)) and not parallel.scene_is_culled(scenes.sd_obj())
+    assert not parallel.scene_is_culled(scenes.mandelbulb()) and not parallel.scene_is_culled(scenes.many_primitives(16))
 
 
 def _worker(rank, world, port, q):

@@ -37,3 +37,20 @@ def test_packed_tables_decode_to_the_reference_tables(oracle_mod):
         c0 = (0 if e == 3 else e) if e < 4 else ((4 if e == 7 else e) if e < 8 else e - 8)
         c1 = (3 if e == 3 else e + 1) if e < 4 else ((7 if e == 7 else e + 1) if e < 8 else e - 4)
         assert (c0, c1) == (corners[2 * e], corners[2 * e + 1])
+
+
+def test_packed_edge_midpoint_offsets_match_the_edge_table():
+    """k_edges' fast vertex keys: the mid-point of edge e in half-voxel units, two bits per edge in SDM_EDGE_DX/DY/DZ
+    (csrc/sdm_kernels.cuh), must be the mean of the edge's two corners (MC_EDGE_TABLE, marching_cubes_constants.cu:3-16;
+    corner offsets of compute_mesh_generation.cu:77-86)."""
+    import pathlib
+    import re
+
+    src = (pathlib.Path(__file__).resolve().parent.parent / "bevy-signed-distance-mesh-generation_b200" / "csrc" / "sdm_kernels.cuh").read_text()
+    words = {ax: int(re.search(r"#define SDM_EDGE_D%s (0x[0-9a-fA-F]+)u" % ax, src).group(1), 16) for ax in "XYZ"}
+    edges = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    corner = lambda c: (2 if c % 4 in (1, 2) else 0, 2 if c % 4 >= 2 else 0, 2 if c >= 4 else 0)
+    for e, (a, b) in enumerate(edges):
+        want = tuple((x + y) // 2 for x, y in zip(corner(a), corner(b)))
+        got = tuple((words[ax] >> (2 * e)) & 3 for ax in "XYZ")
+        assert got == want, (e, got, want)
