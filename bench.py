@@ -377,6 +377,16 @@ def main():
                             "peak_source": peak_src,
                             "algorithmic_bytes": emit_bytes}
 
+    # ---- per-rank view (multi-GPU): shard sizes and device times, to see the balance of the split
+    per_rank = None
+    if dist is not None:
+        mine = {"rank": rank, "finest_voxels": st["level_counts"][levels], "unique_vertices": st["unique_vertices"],
+                "gpu_ms": round(float(sum(kavg.values())), 4),
+                "kernel_ms": {k: round(v, 4) for k, v in kavg.items() if v > 0.02}}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
+
     # ---- checksum of the mesh the timed loop produced (outside the timed region): FNV-1a-64 of the raw bytes, the checksum of
     #      tests/golden; identical at every N because the merged mesh is byte-identical to the single-GPU mesh
     mesh_fnv = None
@@ -412,6 +422,7 @@ def main():
         }
         if world > 1:
             line["exchange"] = exchange
+            line["per_rank"] = per_rank
             line["root_weld_fallback"] = bool(getattr(runner, "last_fallback", False))
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_subvolume_steps(scene_name, scene, bb, init, levels, res, steps=3, warmup=0, target_s=5.0)
@@ -437,14 +448,28 @@ def run_animated(args, bb, init, levels, res, config):
     h = bsdmg_b200.CudaHandler(0, tables[0])
     for f in range(3):
         h.set_scene(tables[f]); h.remesh(bb, init, levels, download=False)
-    wall, gpu, tris = [], [], []
+    wall, gpu, tris, strag, iters = [], [], [], [], []
     for f in range(frames):
         t0 = time.perf_counter()
         h.set_scene(tables[f])
         m = h.remesh(bb, init, levels, download=False)
         wall.append((time.perf_counter() - t0) * 1e3)
-        gpu.append(h.stats()["last_gpu_ms"])
+        st = h.stats()
+        gpu.append(st["last_gpu_ms"]); strag.append(st["stragglers"]); iters.append(st["newton_iterations"])
         tris.append(int(m.triangle_count))
+    # frames far above the median, explained: the same frame again with per-kernel timing (outside the latency statistics)
+    med = float(np.median(wall))
+    outliers = []
+    h.set_profiling(True)
+    for f in [int(i) for i in np.argsort(wall)[::-1][:3] if wall[int(i)] > 2.0 * med]:
+        h.set_scene(tables[f]); h.remesh(bb, init, levels, download=False)
+        kt = {}
+        for name, ms in h.kernel_times():
+            kt[name] = kt.get(name, 0.0) + ms
+        top = sorted(kt.items(), key=lambda kv: -kv[1])[:3]
+        outliers.append({"frame": f, "t": f / 60.0, "wall_ms": round(wall[f], 3), "again_gpu_ms": round(h.stats()["last_gpu_ms"], 3), "stragglers": strag[f],
+                         "newton_iterations": iters[f], "top_kernels_ms": {k: round(v, 3) for k, v in top}})
+    h.set_profiling(False)
     w = np.sort(np.asarray(wall)); g = np.sort(np.asarray(gpu))
     pct = lambda a, p: float(a[min(len(a) - 1, int(round(p / 100.0 * (len(a) - 1))))])
     line = {"metric": f"per-frame remesh latency @{res}^3 (animated scene)", "value": pct(w, 50), "unit": "ms", "n_gpus": 1, "steps": frames, "warmup": 3,
@@ -452,7 +477,10 @@ def run_animated(args, bb, init, levels, res, config):
             "data": "synthetic procedural scene (analytic SDF); no dataset", "config": config,
             "latency_ms": {"p50": pct(w, 50), "p90": pct(w, 90), "p99": pct(w, 99), "max": float(w[-1]), "mean": float(np.mean(w))},
             "gpu_latency_ms": {"p50": pct(g, 50), "p99": pct(g, 99), "max": float(g[-1])},
-            "triangles_per_frame": {"min": int(min(tris)), "max": int(max(tris))}, "gpu_launches": h.stats()["kernel_launches"]}
+            "triangles_per_frame": {"min": int(min(tris)), "max": int(max(tris))}, "gpu_launches": h.stats()["kernel_launches"],
+            "newton": {"stragglers_per_frame": {"p50": int(np.median(strag)), "max": int(max(strag))},
+                       "iterations_per_frame": {"p50": int(np.median(iters)), "max": int(max(iters))}},
+            "outliers": outliers}
     print(json.dumps(line), flush=True)
     h.close()
 

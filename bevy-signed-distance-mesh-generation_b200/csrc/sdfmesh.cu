@@ -20,6 +20,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "sdm_kernels.cuh"
+#include "sdm_render.cuh"
 
 // Device-side clears go through a kernel (one engine for everything on the compute stream; the copy engines are left to the
 // asynchronous mesh download).  `bytes` and `p` must be multiples of 4.
@@ -266,6 +267,7 @@ struct SdmHandle {
     uint32_t table1_entries = 0;        // entries of table1 actually used (adaptive: sized from the previous mesh)
     DevBuf<DevState> state;
     DevState* host_state = nullptr;   // pinned
+    DevBuf<uchar4> render_target;     // sdm_render's RGBA8 image (grow-only, like render_texture_buffer, src/cuda/mod.rs:33)
     DevBuf<uint32_t> shard_range;     // {lo, hi, n} of the last k_take_shard
     uint32_t* host_range = nullptr;   // pinned
     uint32_t shard_index = 0;
@@ -294,7 +296,7 @@ struct SdmHandle {
     int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0, g_edges = 0;
     uint32_t proj_chunk = 256;          // vertex chunk per warp in k_project (SDM_PROJ_CHUNK overrides)
     float slack_factor = 1.0f;         // inflation of the list regions in units of the child voxel size (SDM_SLACK overrides)
-    bool use_lists = true, use_lattice = true;   // SDM_NO_LISTS / SDM_NO_LATTICE: developer switches for A/B measurements
+    bool use_lists = true, use_lattice = true, use_masks = true;   // SDM_NO_LISTS / SDM_NO_LATTICE / SDM_NO_MASKS: developer switches (A/B measurements, tests)
 
     SdmStats stats {};
 
@@ -375,7 +377,7 @@ int configure_kernels(SdmHandle* h) {
         if (per_sm < 1) return fail(SDM_ERR_CUDA, "kernel does not fit on an SM");
         *k.grid = per_sm * h->num_sms;
     }
-    for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project })
+    for (const void* f : { (const void*) k_eval_sdf, (const void*) k_eval_normal, (const void*) k_eval_project, (const void*) k_render })
         CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_for(h, 128), 1024)));
     h->g_light = h->num_sms * 8;
     {   // static-shared-memory kernels of the classification stage
@@ -786,7 +788,7 @@ int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count) {
     h->scene_bytes = (uint32_t) (blob.size() * 16);
     h->scene_nprims = reinterpret_cast<const SceneHeader*>(blob.data())->nprims;
     // culling pays off once the table is long; it needs 1-Lipschitz primitives (not the Mandelbulb estimator)
-    h->mask_capable = !mb && h->scene_nprims > 24;
+    h->mask_capable = !mb && h->scene_nprims > 24 && h->use_masks;
     h->grid.enabled = 0;   // masks depend on the scene: rebuilt on the next remesh
     h->mesh_valid = false;
     // shared-memory sizes / persistent grid sizes only depend on these three: an animated scene (same table shape every
@@ -830,6 +832,7 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         if (const char* e = getenv("SDM_PROJ_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->proj_chunk = (uint32_t) v & ~31u; }
         h->use_lists = getenv("SDM_NO_LISTS") == nullptr;
         h->use_lattice = getenv("SDM_NO_LATTICE") == nullptr;
+        h->use_masks = getenv("SDM_NO_MASKS") == nullptr;   // off: every evaluation folds the whole table (the reference's own semantics)
         SdmPrimitive def[2];
         sdm_scene_default(def, 2);
         rc = sdm_set_scene(h, def, 2);
@@ -863,6 +866,7 @@ void sdm_destroy(SdmHandle* h) {
     h->peer_block.release(); h->peer_local.release();
     h->shard_scratch.release();
     h->shard_range.release();
+    h->render_target.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1653,6 +1657,31 @@ int sdm_shard_weld(SdmHandle* h, uint32_t total_vertices, uint32_t total_triangl
 }
 
 
+// ---- ray-march viewer (CudaHandler::render, src/cuda/mod.rs:348-409) -----------------------------------------------------------
+static_assert(sizeof(SdmRenderGlobals) == sizeof(RenderGlobals) && sizeof(SdmRenderCamera) == sizeof(RenderCamera), "render parameter layouts");
+int sdm_render(SdmHandle* h, const SdmRenderGlobals* globals, const SdmRenderCamera* camera, unsigned char* out_rgba) {
+    if (!h || !globals || !camera || !out_rgba) return fail(SDM_ERR_INVALID, "null argument");
+    const uint32_t w = globals->render_texture_size[0], ht = globals->render_texture_size[1];
+    if (w == 0 || ht == 0 || (w % 8u) || (ht % 16u) || (uint64_t) w * ht > (1ull << 28))
+        return fail(SDM_ERR_INVALID, "image width must be a multiple of 8, height a multiple of 16 (the reference's 8 x 16 pixel blocks)");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_masks_any(h);
+    if (rc) return rc;
+    CK(h->render_target.reserve((size_t) w * ht));
+    RenderGlobals g;
+    RenderCamera c;
+    memcpy(&g, globals, sizeof g);
+    memcpy(&c, camera, sizeof c);
+    NvtxRange nv(h, "render");
+    // grid = (w * h) / BLOCK_SIZE blocks of BLOCK_SIZE threads (src/cuda/mod.rs:382-390)
+    k_render<<<(w * ht) / 128u, 128, smem_for(h, 128), h->stream>>>(h->scene.p, h->render_target.p, g, c, w, ht, h->grid);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_rgba, h->render_target.p, (size_t) w * ht * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SDM_OK;
+}
+
 // ---- peer exchange -------------------------------------------------------------------------------------------------------------
 int sdm_reserve(SdmHandle* h, uint32_t voxel_capacity) {
     if (!h) return fail(SDM_ERR_INVALID, "null handle");
@@ -1806,14 +1835,21 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         CK(dev_fill(s, h->tri_valid_bits.p, 0, ((size_t) h->cap_uniq / 32 + 2) * 4));
         k_peer_apply_mark<<<h->g_light, 256, 0, s>>>(ctl, rank, par, pairs, h->tri_valid_bits.p, h->vidx.p, h->peer_local.p);
         k_scan_bits_1block_dev<<<1, 1024, 0, s>>>(h->tri_valid_bits.p, h->tri_prefix.p, &ctl->hdr[par][rank].V);
-        const bool global = deliver == 0;
-        float* dpos = global ? h->root_pos : h->out_pos[1].p;
-        float* dnrm = global ? h->root_nrm : h->out_nrm[1].p;
-        uint32_t* didx = global ? h->root_idx : h->out_idx[1].p;
-        k_peer_apply_vertices<<<h->g_light * 2, 256, 0, s>>>(ctl, rank, par, h->tri_valid_bits.p, h->tri_prefix.p, h->out_pos[0].p, h->out_nrm[0].p, dpos, dnrm, global ? 1u : 0u);
-        k_peer_apply_indices<<<h->g_light * 2, 256, 0, s>>>(ctl, rank, par, h->tri_valid_bits.p, h->tri_prefix.p, h->vidx.p, h->out_idx[0].p, didx, global ? 1u : 0u);
-        k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagD[rank], epoch);
+        // Rank 0 writes its rows where they belong (its second output set IS the merged mesh when deliver = 0); the other ranks compact
+        // into their own second set and, for deliver = 0, push it to rank 0 in one coalesced copy.
+        const bool direct = deliver == 0 && rank == 0;
+        k_peer_apply_vertices<<<h->g_light * 2, 256, 0, s>>>(ctl, rank, par, h->tri_valid_bits.p, h->tri_prefix.p, h->out_pos[0].p, h->out_nrm[0].p, h->out_pos[1].p,
+                                                             h->out_nrm[1].p, direct ? 1u : 0u);
+        k_peer_apply_indices<<<h->g_light * 2, 256, 0, s>>>(ctl, rank, par, h->tri_valid_bits.p, h->tri_prefix.p, h->vidx.p, h->out_idx[0].p, h->out_idx[1].p,
+                                                            direct ? 1u : 0u);
         mark(h, "peer_apply");
+        if (deliver == 0 && rank != 0) {
+            k_peer_push<<<h->num_sms * 4, 256, 0, s>>>(ctl, rank, par, reinterpret_cast<const uint32_t*>(h->out_pos[1].p), reinterpret_cast<const uint32_t*>(h->out_nrm[1].p),
+                                                       h->out_idx[1].p, reinterpret_cast<uint32_t*>(h->root_pos), reinterpret_cast<uint32_t*>(h->root_nrm), h->root_idx);
+            mark(h, "peer_push");
+            h->stats.kernel_launches++;
+        }
+        k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagD[rank], epoch);
         h->stats.kernel_launches += 6 + (spin ? 1 : 0);
     }
     if (phase_mask & 16u) {   // P4: rank 0 waits for everybody's rows; totals for the host

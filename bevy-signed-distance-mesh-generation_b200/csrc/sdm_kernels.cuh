@@ -1168,42 +1168,45 @@ __global__ void __launch_bounds__(256) k_soup(DevState* st, int level, const uin
 // Restrict the list of `level` to the contiguous part [n*shard/count, n*(shard+1)/count) (64-bit arithmetic),
 // copied to the front of the other ping-pong buffer.  Children keep their parent's order (compute_mesh_generation.cu:51)
 // and level 0 is x-major (src/cuda/mod.rs:110-119), so a contiguous part of the list is an x-slab at every level.
-// Shard bounds in the DENSE level-0 list weighted by the cells' "may contain the surface" flags (k_build_masks): every shard gets the
-// same number of flagged cells, so that no level has to be refined redundantly to find a balanced split.  bounds[0..1] = [lo, hi);
-// the same arithmetic on every rank, so the shards tile the list.
+// Shard bounds in the DENSE level-0 list by the cells' weights (k_build_masks: 0 = provably no surface, else the number of primitives
+// the cell keeps): every shard gets the same total weight, so that no level has to be refined redundantly to find a balanced split
+// and shards in dense regions - longer primitive lists per evaluation - get fewer voxels.  bounds[0..1] = [lo, hi); the same
+// arithmetic on every rank, so the shards tile the list.
 __global__ void __launch_bounds__(1024) k_shard_bounds_by_flags(const uint8_t* __restrict__ flags, uint32_t n, uint32_t shard, uint32_t count, uint32_t* bounds) {
-    __shared__ uint32_t s_part[1024];
+    __shared__ unsigned long long s_part[1024];
     const uint32_t per = (n + 1023u) / 1024u, i0 = min(threadIdx.x * per, n), i1 = min(i0 + per, n);
-    uint32_t sum = 0;
-    if ((per & 15u) == 0u && i1 - i0 == per && (reinterpret_cast<uintptr_t>(flags) & 15u) == 0u) {   // 16 flags per load (they are 0 / 1 bytes)
+    unsigned long long sum = 0;
+    if ((per & 15u) == 0u && i1 - i0 == per && (reinterpret_cast<uintptr_t>(flags) & 15u) == 0u) {   // 16 weights per load
         const uint4* f4 = reinterpret_cast<const uint4*>(flags + i0);
         for (uint32_t q = 0; q < per / 16u; q++) {
             const uint4 w = __ldg(f4 + q);
-            sum += __popc(w.x & 0x01010101u) + __popc(w.y & 0x01010101u) + __popc(w.z & 0x01010101u) + __popc(w.w & 0x01010101u);
+            sum += __dp4a(w.x, 0x01010101u, 0u) + __dp4a(w.y, 0x01010101u, 0u) + __dp4a(w.z, 0x01010101u, 0u) + __dp4a(w.w, 0x01010101u, 0u);
         }
     } else {
-        for (uint32_t i = i0; i < i1; i++) sum += flags[i] ? 1u : 0u;
+        for (uint32_t i = i0; i < i1; i++) sum += flags[i];
     }
     s_part[threadIdx.x] = sum;
     __syncthreads();
     for (uint32_t o = 1; o < 1024u; o <<= 1) {
-        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        const unsigned long long v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0ull;
         __syncthreads();
         s_part[threadIdx.x] += v;
         __syncthreads();
     }
-    const uint32_t total = s_part[1023], before = s_part[threadIdx.x] - sum;
+    const unsigned long long total = s_part[1023], before = s_part[threadIdx.x] - sum;
     if (threadIdx.x == 0) { bounds[0] = 0; bounds[1] = n; }   // shard 0 starts at 0, the last one ends at n; also the answer when nothing is flagged
     __syncthreads();
-    // boundary b (b = shard, shard + 1) = index of flagged cell number total * b / count; whoever holds it writes it
+    // boundary b (b = shard, shard + 1) = the cell in which the running weight passes total * b / count; whoever holds it writes it
     for (uint32_t b = 0; b < 2u; b++) {
         const uint32_t which = shard + b;
-        if (which == 0u || which == count || total == 0u) continue;
-        const uint32_t target = (uint32_t) ((uint64_t) total * which / count);
+        if (which == 0u || which == count || total == 0ull) continue;
+        const unsigned long long target = total * which / count;
         if (target >= before && target < before + sum) {
-            uint32_t seen = before;
-            for (uint32_t i = i0; i < i1; i++)
-                if (flags[i]) { if (seen == target) { bounds[b] = i; break; } seen++; }
+            unsigned long long seen = before;
+            for (uint32_t i = i0; i < i1; i++) {
+                seen += flags[i];
+                if (seen > target) { bounds[b] = i; break; }
+            }
         }
     }
 }
@@ -1610,6 +1613,18 @@ __global__ void __launch_bounds__(256) k_peer_apply_indices(const PeerCtl* ctl, 
         dst_idx[base + j] = ((bitmap[c >> 5] >> (c & 31u)) & 1u) ? remap[c] : goff + c - bit_rank(bitmap, prefix, c);
     }
 }
+// deliver = 0: this rank's final rows (compacted in its own second output set) go to rank 0's output set at their global offsets as
+// plain coalesced word copies - 128 contiguous bytes per warp store, the packet size NVLink likes (12-byte stores scattered by
+// k_peer_apply_* straight into the peer took three times as long).  which: 0 positions, 1 normals, 2 indices.
+__global__ void __launch_bounds__(256) k_peer_push(const PeerCtl* ctl, uint32_t rank, uint32_t parity, const uint32_t* __restrict__ src_pos, const uint32_t* __restrict__ src_nrm,
+                                                   const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ dst_pos, uint32_t* __restrict__ dst_nrm, uint32_t* __restrict__ dst_idx) {
+    if (ctl->status[parity]) return;
+    const size_t nv = 3 * (size_t) (ctl->goff[parity][rank + 1] - ctl->goff[parity][rank]), nt = 3 * (size_t) ctl->hdr[parity][rank].T;
+    const size_t ov = 3 * (size_t) ctl->goff[parity][rank], ot = 3 * (size_t) ctl->toff[parity][rank];
+    const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = tid; i < nv; i += stride) { dst_pos[ov + i] = src_pos[i]; dst_nrm[ov + i] = src_nrm[i]; }
+    for (size_t i = tid; i < nt; i += stride) dst_idx[ot + i] = src_idx[i];
+}
 // totals for the host of rank 0 (and of every rank, for bookkeeping)
 __global__ void k_peer_totals(const PeerCtl* ctl, uint32_t world, uint32_t parity, PeerLocal* local) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1852,7 +1867,11 @@ __global__ void __launch_bounds__(256) k_build_masks_fine(const uint4* __restric
         }
         if (out_maybe) {   // zero-crossing flag: |sd(p) - sd(c)| <= rho on the cell, acc is sd(c) to ~1e-5
             const bool empty = fabsf(acc) > rho + 1e-4f;
-            out_maybe[((size_t) ix * g.G + iy) * g.G + iz] = empty ? 0 : 1;   // NaN: not empty
+            // non-zero = may contain the surface; the value is the number of primitives the cell keeps (1..255), which the multi-GPU
+            // split uses as the cell's weight: the cost of a surface voxel grows with the length of its primitive list
+            uint32_t kept = 0;
+            for (uint32_t w = 0; w < g.W; w++) kept += __popc(rows[lane * 33u + w]);
+            out_maybe[((size_t) ix * g.G + iy) * g.G + iz] = empty ? 0 : (uint8_t) max(1u, min(255u, kept));   // NaN: not empty
         }
         __syncwarp();
     }

@@ -78,6 +78,15 @@ class _ShardBuffers(ctypes.Structure):
                 ("capacity_vertices", ctypes.c_uint32), ("capacity_triangles", ctypes.c_uint32)]
 
 
+class _RenderGlobals(ctypes.Structure):   # GlobalsBuffer, bindings.h:16-21
+    _fields_ = [("tick", ctypes.c_ulonglong), ("time", ctypes.c_float), ("render_texture_size", ctypes.c_uint * 2), ("render_screen_size", ctypes.c_float * 2)]
+
+
+class _RenderCamera(ctypes.Structure):    # CameraBuffer, bindings.h:23-29
+    _fields_ = [("position", ctypes.c_float * 3), ("forward", ctypes.c_float * 3), ("up", ctypes.c_float * 3), ("right", ctypes.c_float * 3),
+                ("fov", ctypes.c_float)]
+
+
 class _PeerExport(ctypes.Structure):
     _fields_ = [("handle", (ctypes.c_ubyte * 64) * 4), ("block_bytes", ctypes.c_uint64), ("cap_vertices", ctypes.c_uint32),
                 ("cap_triangles", ctypes.c_uint32), ("cap_rows", ctypes.c_uint32), ("world", ctypes.c_uint32)]
@@ -100,7 +109,7 @@ ABI_SYMBOLS = [
     "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_fixup",
     "sdm_shard_welded_buffers", "sdm_shard_reserve_welded",
     "sdm_mesh_save_obj", "sdm_hash_bytes", "sdm_reserve", "sdm_peer_root_export", "sdm_peer_attach", "sdm_peer_step", "sdm_peer_finish",
-    "sdm_peer_download_async",
+    "sdm_peer_download_async", "sdm_render",
     "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
 
@@ -413,6 +422,15 @@ class CudaHandler:
     def save_obj(self, m, path) -> None:
         """sdm_mesh_save_obj of a device-resident mesh (`remesh(..., download=False)`)."""
         self._check(self._lib.sdm_mesh_save_obj(self._h, ctypes.byref(m), str(path).encode()))
+
+    # -- ray-march viewer -----------------------------------------------------------------------------------------------------
+    def render(self, width: int, height: int, position, forward, up, right, fov: float, screen_size=None, tick: int = 0, time: float = 0.0) -> np.ndarray:
+        """``CudaHandler::render`` (src/cuda/mod.rs:348-409): (height, width, 4) uint8 image of the handle's current scene."""
+        g = _RenderGlobals(tick, time, (ctypes.c_uint * 2)(width, height), (ctypes.c_float * 2)(*(screen_size or (float(width), float(height)))))
+        c = _RenderCamera((ctypes.c_float * 3)(*position), (ctypes.c_float * 3)(*forward), (ctypes.c_float * 3)(*up), (ctypes.c_float * 3)(*right), fov)
+        out = np.empty((height, width, 4), np.uint8)
+        self._check(self._lib.sdm_render(self._h, ctypes.byref(g), ctypes.byref(c), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
 
     # -- peer exchange (include/sdfmesh.h): the distributed weld driven from the device -------------------------------
     def reserve(self, voxel_capacity: int) -> None:

@@ -132,7 +132,7 @@ def peer_capacities(total_vertices: int, total_triangles: int, world: int):
     mesh (2 vertices / 3 triangles per voxel of capacity), with a quarter of head room; a rank's interface candidates are a fraction
     of its vertices."""
     cap_vox = int(max(total_vertices / 2.0, total_triangles / 3.0) * 1.25) + 4096
-    cap_rows = max(1 << 16, int(total_vertices / max(world, 1) / 2))
+    cap_rows = max(1 << 16, int(total_vertices / max(world, 1) / 4))
     return cap_vox, cap_rows
 
 

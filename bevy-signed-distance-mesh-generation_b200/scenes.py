@@ -35,6 +35,11 @@ def sd_obj() -> np.ndarray:
     )
 
 
+def render_scene() -> np.ndarray:
+    """sd_scene of the ray-march viewer (compute_render.cu:3-19): min(sd_obj, wire box of the meshing domain with lw 0.05)."""
+    return np.concatenate([sd_obj(), np.stack([_prim(BOX_SKELETON, FOLD_MIN, radius=0.05, a=(0, 0, 0), b=(5.0, 5.0, 5.0))])])
+
+
 def sphere_box() -> np.ndarray:
     """C1: min(length(p-(0.6,0,0)) - 1, sd_box(p, (-0.6,0,0), (1.5,1.5,1.5))) (signed_distance.cu:82-91 forms)."""
     return np.stack(

@@ -240,6 +240,17 @@ int sdm_shard_resolve(SdmHandle* h, const uint32_t* rows_device, uint32_t total_
                       uint32_t* out_removed /* [shard_count] */);
 int sdm_shard_fixup(SdmHandle* h, const uint32_t* triangle_counts /* [shard_count of the last sdm_shard_resolve] */, SdmMesh* out_mesh);
 
+/* ---- ray-march viewer (CudaHandler::render, src/cuda/mod.rs:348-409; kernel compute_render, cuda/modules/compute_render.cu:21-97) ----
+ * Sphere-traces the handle's current scene (<= 256 steps, depth limit 500, pixel-cone collision test), shades hits with the
+ * finite-difference normal and the reference's two-colour ramp, ACES tone map, RGBA8.  The by-value structs have the layouts of
+ * GlobalsBuffer / CameraBuffer (bindings.h:16-29).  The image is render_texture_size[0] x render_texture_size[1] (width a multiple
+ * of 8, height a multiple of 16: the reference's 8 x 16 pixel blocks, common.cu:186-215); out_rgba = 4 * w * h host bytes.
+ * The reference draws sd_obj plus the wire box of the meshing domain (compute_render.cu:3-19): that scene is the table
+ * { BOX_SKELETON(0,(3,1,.5),.1) min, SPHERE(0,1) smooth_min .5, BOX_SKELETON(0,(5,5,5),.05) min }. */
+typedef struct SdmRenderGlobals { unsigned long long tick; float time; unsigned int render_texture_size[2]; float render_screen_size[2]; } SdmRenderGlobals;
+typedef struct SdmRenderCamera { float position[3]; float forward[3]; float up[3]; float right[3]; float fov; } SdmRenderCamera;
+int sdm_render(SdmHandle* h, const SdmRenderGlobals* globals, const SdmRenderCamera* camera, unsigned char* out_rgba);
+
 /* ---- peer exchange: the distributed weld without the host (one process per GPU on one node) ---------------------------------
  * The calls above route every count through the host.  Here rank 0 exports a control block, per-rank key-row slots and its second
  * output set (CUDA IPC); the other ranks map them, and one step runs from the first kernel to the last with device-side flags

@@ -322,3 +322,27 @@ class RefGpu:
         rc = self.lib.refgpu_sdf(ctypes.c_int(scene), _fp(pts), ctypes.c_uint32(pts.shape[0]), _fp(out))
         assert rc == 0
         return out
+
+
+class RefRender:
+    """The reference's ray-march module (cuda/modules/compute_render.cu) compiled by path for sm_100a with IEEE flags
+    (oracle/_ref/libref_render.so)."""
+
+    def __init__(self):
+        path = HERE / "_ref" / "libref_render.so"
+        if not path.exists():
+            raise FileNotFoundError(str(path))
+        self.lib = ctypes.CDLL(str(path))
+
+    @staticmethod
+    def available() -> bool:
+        return (HERE / "_ref" / "libref_render.so").exists()
+
+    def layout(self):
+        return dict(globals=int(self.lib.refrender_sizeof_globals()), camera=int(self.lib.refrender_sizeof_camera()))
+
+    def render(self, globals_struct, camera_struct, width, height):
+        out = np.empty((height, width, 4), np.uint8)
+        rc = self.lib.refrender(ctypes.byref(globals_struct), ctypes.byref(camera_struct), out.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        return out
