@@ -551,10 +551,16 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     const bool inherit = lists && h->lists_level == h->level;
     const float delta = lists ? (h->delta_override > 0.0f ? h->delta_override : h->slack_factor * std::max(ox, std::max(oy, oz))) : 0.0f;
     NvtxRange nv(h, "refine level", h->level);
+    // dense level of a culled scene: only the parents whose cells may contain the surface are evaluated, in full tiles
+    const bool gather0 = h->level == 0 && h->grid.enabled && h->grid.maybe != nullptr;
+    if (gather0) {
+        k_active_parents<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p, h->tri_off.p);
+        h->stats.kernel_launches++;
+    }
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p,
-                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, h->level == 0 && h->grid.enabled ? 1 : 0,
+                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, 0,
                                                                 inherit ? h->vl[h->vl_cur].p : nullptr, inherit ? h->vparent[h->vp_cur].p : nullptr,
-                                                                lists ? h->vl[h->vl_cur ^ 1].p : nullptr, delta);
+                                                                lists ? h->vl[h->vl_cur ^ 1].p : nullptr, delta, gather0 ? h->tri_off.p : nullptr);
     mark(h, "k_refine");
     k_refine_emit<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cap_vox,
                                                      ox, oy, oz, h->m27.p, with_cases ? h->cases.p : nullptr, lists ? h->vparent[h->vp_cur ^ 1].p : nullptr);

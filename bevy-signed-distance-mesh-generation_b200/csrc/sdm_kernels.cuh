@@ -48,6 +48,7 @@ struct DevState {
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
     uint32_t cases_from_refine; // epoch of the last k_refine that met an inexact lattice (its case indices must not be used)
     uint32_t weld_dups;         // vertices whose quantised weld key was already in the table (0: the weld merges nothing)
+    uint32_t n_active0;         // dense level of a culled scene: parents whose cells may contain the surface (k_active_parents)
     uint32_t n_escaped;         // vertices whose Newton iterate left the region their inherited list is proven for (general path)
     uint32_t list_fallbacks;    // tiles of the mesh stage that had to use the cell masks instead of inherited lists
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k_init_field(float* __restrict__ vox, Dev
     const uint64_t n = (uint64_t) init * init * init;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->level_count[0] = (uint32_t) (n <= cap_vox ? n : 0);
+        st->n_active0 = 0;
         if (n > cap_vox) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
     }
     if (n > cap_vox) return;
@@ -120,6 +122,31 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 // append fused in, a third of the kernel's instructions were look-back spins: ncu, profiles/).
 // k_refine_emit: surviving children are appended in the reference's order (n_id = id*8 + i*4 + j*2 + k, :51; Vec::retain
 // is stable, src/cuda/mod.rs:192) at the offset given by a block scan + decoupled look-back across tiles - a streaming pass.
+// Dense level of a culled scene: most parents lie in cells that provably contain no zero crossing - 27 equal signs, no child
+// survives (is_border, :36-49).  They get their "all outside" sign word here, and the indices of the others are gathered so that
+// k_refine works on full tiles of parents that need evaluating (with the test inside k_refine a tile of 32 consecutive cells had
+// ~5 busy lanes: 156 M warp instructions for level 0 of the 1 024-primitive scene, ncu).  The order of the gathered indices
+// does not matter: k_refine writes each parent's sign word at the parent's own index.
+__global__ void __launch_bounds__(256) k_active_parents(const float* __restrict__ in_vox, DevState* st, int level, float osx, float osy, float osz, MaskGrid grid,
+                                                        uint32_t* __restrict__ out_m27, uint32_t* __restrict__ out_idx) {
+    const uint32_t n = st->level_count[level];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+        bool may = false;
+        if (p < n) {
+            const float bx = in_vox[3 * (size_t) p], by = in_vox[3 * (size_t) p + 1], bz = in_vox[3 * (size_t) p + 2];
+            may = box_may_cross(grid, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
+            if (!may) out_m27[p] = 0u;
+        }
+        const uint32_t ball = __ballot_sync(0xffffffffu, may);
+        uint32_t base = 0;
+        if (lane == 0 && ball) base = atomicAdd(&st->n_active0, (uint32_t) __popc(ball));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (may) out_idx[base + __popc(ball & ((1u << lane) - 1u))] = p;
+    }
+}
+
 #ifndef SDM_REFINE_MINB
 #define SDM_REFINE_MINB 3
 #endif
@@ -128,11 +155,12 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
                                                 uint32_t cases_epoch /* 0: no case indices wanted */, int use_cell_flags,
                                                 const uint4* __restrict__ vl_in /* records of the previous level's parents, or null */,
                                                 const uint32_t* __restrict__ vparent_in /* record index per voxel of this level */,
-                                                uint4* __restrict__ vl_out /* one record per voxel of this level, or null */, float delta) {
+                                                uint4* __restrict__ vl_out /* one record per voxel of this level, or null */, float delta,
+                                                const uint32_t* __restrict__ active_idx /* k_active_parents' list: only these parents, or null: all */) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = st->level_count[level];
+    const uint32_t n = active_idx ? st->n_active0 : st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
     const bool want_cases = cases_epoch != 0u;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->ticket[TK_REFINE_EMIT] = 0;   // k_refine_emit runs after this kernel
@@ -150,11 +178,12 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
         const uint32_t p0 = tile << 5;
         const uint32_t np = min(32u, n - p0);
         const bool active = lane < np;
+        const uint32_t p = active ? (active_idx ? active_idx[p0 + lane] : p0 + lane) : 0u;   // this lane's parent
         float bx = 0.f, by = 0.f, bz = 0.f;
         if (active) {
-            bx = in_vox[3 * (size_t) (p0 + lane) + 0];
-            by = in_vox[3 * (size_t) (p0 + lane) + 1];
-            bz = in_vox[3 * (size_t) (p0 + lane) + 2];
+            bx = in_vox[3 * (size_t) p + 0];
+            by = in_vox[3 * (size_t) p + 1];
+            bz = in_vox[3 * (size_t) p + 2];
         }
         // Dense level of a culled scene: a parent inside cells that provably contain no zero crossing has 27 equal signs, so
         // none of its children survives (is_border, :36-49) - it is not evaluated and does not lengthen the tile's list.
@@ -169,12 +198,12 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
             // by delta (+ the empirical_normal stencil reach of the mesh stage, 2e-3) - one pass over the candidates decides both
             const float lx = bx, ly = by, lz = bz;
             const float hx = bx + 2.0f * osx, hy = by + 2.0f * osy, hz = bz + 2.0f * osz;
-            uint16_t* own = vl_out ? reinterpret_cast<uint16_t*>(vl_out + 2 * (size_t) (p0 + lane)) : nullptr;   // warp-uniform null / non-null
+            uint16_t* own = vl_out ? reinterpret_cast<uint16_t*>(vl_out + 2 * (size_t) p) : nullptr;   // warp-uniform null / non-null
             uint32_t ncand = SDM_TLIST_NONE;
             if (vl_in) {
                 uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = lo;
                 if (eval) {
-                    const uint32_t pi = vparent_in[p0 + lane];
+                    const uint32_t pi = vparent_in[p];
                     lo = __ldg(vl_in + 2 * (size_t) pi); hi = __ldg(vl_in + 2 * (size_t) pi + 1);
                 }
                 ncand = tile_union_lists(sc, lo, hi);
@@ -201,7 +230,7 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
             }
         }
         if (active) {
-            out_m27[p0 + lane] = m27;   // a skipped parent: 27 equal signs, recorded as "all outside" (no child survives either way)
+            out_m27[p] = m27;   // a skipped parent: 27 equal signs, recorded as "all outside" (no child survives either way)
             if (want_cases) {
                 // The mesh stage samples child corners at child_base + size (compute_mesh_generation.cu:77-86); the lattice
                 // has base + 2*size where the child is the upper one.  The 27 signs double as the children's corner signs
@@ -803,20 +832,26 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
         NewtonCycle cyc;
         cyc.sx = r.s[0]; cyc.sy = r.s[1]; cyc.sz = r.s[2]; cyc.power = r.power; cyc.lam = r.lam; cyc.stop_at = r.stop_at;
         running = running && it < cyc.stop_at;
-        // The tile's primitive list is built for a ball of extra radius SLACK around each iterate and kept until an iterate
+        // The tile's primitive list is built for a ball of extra radius `slack` around each iterate and kept until an iterate
         // leaves its ball (or a half finishes): a slow orbit moves ~1e-4 per step, so the list is rebuilt every ~100 steps
-        // instead of every step.  (A larger ball only makes the list a superset: still exact.)
-        const float SLACK = 0.01f;
+        // instead of every step.  (A larger ball only makes the list a superset: still exact.)  An orbit that keeps JUMPING -
+        // between the two sides of a crease, say - would rebuild on every step (an animated frame spent 157 of its 171 ms on one such
+        // vertex): when rebuilds come in quick succession the ball doubles, up to what the cell look-up covers, until it holds the orbit.
+        float slack = 0.01f;
+        const float max_slack = grid.enabled ? 1.5f * grid.cell : 0.01f;
+        uint32_t recent = 0, since = 0;
         float lcx = gx, lcy = gy, lcz = gz;
         bool list_valid = false;
         while (__any_sync(0xffffffffu, running)) {
             const float mvx = gx - lcx, mvy = gy - lcy, mvz = gz - lcz;
-            const bool moved = running && !(mvx * mvx + mvy * mvy + mvz * mvz <= (0.5f * SLACK) * (0.5f * SLACK));   // NaN -> rebuild
+            const bool moved = running && !(mvx * mvx + mvy * mvy + mvz * mvz <= (0.5f * slack) * (0.5f * slack));   // NaN -> rebuild
             if (!list_valid || __any_sync(0xffffffffu, moved)) {
-                tile_mask_from_point(grid, sc, running && hl == 0, gx, gy, gz, SLACK);
+                if (list_valid && ++recent >= 4u && slack < max_slack) { slack = fminf(2.0f * slack, max_slack); recent = 0; }
+                tile_mask_from_point(grid, sc, running && hl == 0, gx, gy, gz, slack);
                 lcx = gx; lcy = gy; lcz = gz;
                 list_valid = true;
             }
+            if (++since >= 64u) { since = 0; recent >>= 1; }   // rebuilds far apart do not add up
             if (lane == 0) work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, running && hl == 0));
             else (void) __ballot_sync(0xffffffffu, running && hl == 0);
             // half-lane 0: the iterate; half-lane 1 + 4*axis + s: stencil point s of that axis (same construction as normal_points)

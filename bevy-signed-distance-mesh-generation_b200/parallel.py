@@ -127,12 +127,13 @@ def emulated_peer_step(handlers, bb_size, init_factor, levels, split_level, epoc
     return [h.peer_finish() for h in handlers]
 
 
-def peer_capacities(total_vertices: int, total_triangles: int, world: int):
+def peer_capacities(total_vertices: int, total_triangles: int, world: int, max_shard_vertices: int = 0):
     """(voxel capacity of rank 0, key rows per rank) for a merged mesh of the given size: rank 0's second output set must hold the whole
-    mesh (2 vertices / 3 triangles per voxel of capacity), with a quarter of head room; a rank's interface candidates are a fraction
-    of its vertices."""
+    mesh (2 vertices / 3 triangles per voxel of capacity), with a quarter of head room.  A rank's interface candidates are its vertices
+    inside another shard's x range: where a shard boundary cuts through a layer of level-0 cells the ranges overlap by a whole cell, which
+    can be a third of a thin shard - so a slot holds a whole (even) shard and a half."""
     cap_vox = int(max(total_vertices / 2.0, total_triangles / 3.0) * 1.25) + 4096
-    cap_rows = max(1 << 16, int(total_vertices / max(world, 1) / 4))
+    cap_rows = max(1 << 16, int(total_vertices / max(world, 1) * 1.5), int(max_shard_vertices * 1.25))
     return cap_vox, cap_rows
 
 
@@ -161,7 +162,9 @@ class PeerRemesher:
         allc = torch.empty((world, 2), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allc, mine)
         totals = allc.sum(dim=0).cpu().tolist()
-        self.cap_vox, self.cap_rows = peer_capacities(int(totals[0]), int(totals[1]), world)
+        # (wandering Newton iterates can stretch a shard's x range over the whole domain - Mandelbulb - and then every vertex of the
+        # other shards is an interface candidate: a slot must hold the largest shard)
+        self.cap_vox, self.cap_rows = peer_capacities(int(totals[0]), int(totals[1]), world, int(allc[:, 0].max().item()))
         if rank == 0:
             h.reserve(self.cap_vox)
         blob = [h.peer_root_export(world, self.cap_rows) if rank == 0 else None]
