@@ -283,6 +283,11 @@ struct SdmHandle {
     uint32_t* root_idx = nullptr;
     uint32_t peer_rank = 0, peer_world = 0, peer_cap_rows = 0, peer_cap_v = 0, peer_cap_t = 0;
     void* ipc_mapped[4] = { nullptr, nullptr, nullptr, nullptr };
+    DevBuf<float> peer_frac;          // cumulative weight fractions of the shards, two generations of SDM_PEER_MAX + 1 (k_peer_rebalance)
+    DevBuf<unsigned long long> peer_t0;
+    const float* shard_frac = nullptr;   // fractions the next enqueue_take_shard uses (null: equal shares)
+    uint32_t peer_last_epoch = 0;
+    bool peer_rebalance = true;       // SDM_NO_REBALANCE switches the measured load balancing off
     DevBuf<PeerLocal> peer_local;
     PeerLocal* host_peer_local = nullptr;   // pinned
     int peer_deliver = 0;
@@ -551,16 +556,10 @@ int enqueue_refine(SdmHandle* h, bool with_cases = false) {
     const bool inherit = lists && h->lists_level == h->level;
     const float delta = lists ? (h->delta_override > 0.0f ? h->delta_override : h->slack_factor * std::max(ox, std::max(oy, oz))) : 0.0f;
     NvtxRange nv(h, "refine level", h->level);
-    // dense level of a culled scene: only the parents whose cells may contain the surface are evaluated, in full tiles
-    const bool gather0 = h->level == 0 && h->grid.enabled && h->grid.maybe != nullptr;
-    if (gather0) {
-        k_active_parents<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p, h->tri_off.p);
-        h->stats.kernel_launches++;
-    }
     k_refine<<<h->g_refine, 256, smem_for(h, 256), h->stream>>>(h->scene.p, h->vox[h->cur].p, h->state.p, h->level, ox, oy, oz, h->grid, h->m27.p,
-                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, 0,
+                                                                with_cases ? (h->cases_epoch = next_epoch(h)) : 0u, h->level == 0 && h->grid.enabled ? 1 : 0,
                                                                 inherit ? h->vl[h->vl_cur].p : nullptr, inherit ? h->vparent[h->vp_cur].p : nullptr,
-                                                                lists ? h->vl[h->vl_cur ^ 1].p : nullptr, delta, gather0 ? h->tri_off.p : nullptr);
+                                                                lists ? h->vl[h->vl_cur ^ 1].p : nullptr, delta);
     mark(h, "k_refine");
     k_refine_emit<<<h->g_light, 256, 0, h->stream>>>(h->vox[h->cur].p, h->vox[h->cur ^ 1].p, h->state.p, h->level, next_epoch(h), h->tiles.p, h->cap_vox,
                                                      ox, oy, oz, h->m27.p, with_cases ? h->cases.p : nullptr, lists ? h->vparent[h->vp_cur ^ 1].p : nullptr);
@@ -582,7 +581,8 @@ int enqueue_take_shard(SdmHandle* h, uint32_t shard_index, uint32_t shard_count)
     const bool vp = h->lists_level == h->level;   // the shard's voxels keep their record indices
     const uint32_t* bounds = nullptr;
     if (h->level == 0 && h->grid.enabled && h->grid.maybe && h->grid.G == h->field_init && shard_count > 1) {
-        k_shard_bounds_by_flags<<<1, 1024, 0, h->stream>>>(h->grid.maybe, h->grid.G * h->grid.G * h->grid.G, shard_index, shard_count, h->shard_range.p + 4);
+        k_shard_bounds_by_flags<<<1, 1024, 0, h->stream>>>(h->grid.maybe, h->grid.G * h->grid.G * h->grid.G, shard_index, shard_count, h->shard_range.p + 4,
+                                                            h->shard_frac);
         bounds = h->shard_range.p + 4;
         h->stats.kernel_launches++;
     }
@@ -869,7 +869,7 @@ void sdm_destroy(SdmHandle* h) {
     if (h->host_scratch) cudaFreeHost(h->host_scratch);
     if (h->host_peer_local) cudaFreeHost(h->host_peer_local);
     for (void* m : h->ipc_mapped) if (m) cudaIpcCloseMemHandle(m);
-    h->peer_block.release(); h->peer_local.release();
+    h->peer_block.release(); h->peer_local.release(); h->peer_frac.release(); h->peer_t0.release();
     h->shard_scratch.release();
     h->shard_range.release();
     h->render_target.release();
@@ -1704,6 +1704,10 @@ static size_t peer_pairs_offset(uint32_t world, uint32_t cap_rows) { return peer
 static size_t peer_block_bytes(uint32_t world, uint32_t cap_rows) { return peer_pairs_offset(world, cap_rows) + (size_t) 2 * world * cap_rows * sizeof(uint2); }
 static int peer_common_alloc(SdmHandle* h) {
     CK(h->peer_local.reserve(1));
+    CK(h->peer_frac.reserve(2 * (SDM_PEER_MAX + 1)));
+    CK(h->peer_t0.reserve(1));
+    h->peer_last_epoch = 0;
+    h->peer_rebalance = getenv("SDM_NO_REBALANCE") == nullptr;
     if (!h->host_peer_local) CK(cudaMallocHost(&h->host_peer_local, sizeof(PeerLocal)));
     return ensure_shard_scratch(h);
 }
@@ -1781,6 +1785,15 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         if ((uint64_t) p.init_factor * p.init_factor * p.init_factor > h->cap_vox) return fail(SDM_ERR_CAPACITY, "sdm_reserve first");
         prof_begin(h);
         CK(cudaEventRecord(h->ev0, s));
+        k_peer_mark_start<<<1, 32, 0, s>>>(h->peer_t0.p);
+        {   // shard fractions of this step from the compute times of the previous one (consecutive epochs only)
+            float* fnew = h->peer_frac.p + (size_t) par * (SDM_PEER_MAX + 1);
+            const float* fprev = h->peer_frac.p + (size_t) (par ^ 1u) * (SDM_PEER_MAX + 1);
+            k_peer_rebalance<<<1, 32, 0, s>>>(ctl, par ^ 1u, world, fprev, fnew, (h->peer_rebalance && h->peer_last_epoch + 1 == epoch && epoch > 1) ? 1 : 0);
+            h->shard_frac = fnew;
+            h->peer_last_epoch = epoch;
+            h->stats.kernel_launches += 2;
+        }
         rc = reset_state(h);
         if (rc) return rc;
         mark(h, "start");
@@ -1788,8 +1801,9 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         if (rc) return rc;
         h->delta_override = h->slack_factor * ldexpf(p.bb_size / (float) p.init_factor, -(int) p.levels);
         for (uint32_t l = 0; l < split_level && !rc; l++) rc = enqueue_refine(h);
-        if (rc) { h->delta_override = 0.0f; return rc; }
+        if (rc) { h->delta_override = 0.0f; h->shard_frac = nullptr; return rc; }
         rc = enqueue_take_shard(h, rank, world);
+        h->shard_frac = nullptr;
         if (rc) { h->delta_override = 0.0f; return rc; }
         for (uint32_t l = split_level; l < p.levels && !rc; l++) rc = enqueue_refine(h, l + 1 == p.levels);
         h->delta_override = 0.0f;
@@ -1801,7 +1815,7 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         if (rc) return rc;
         k_shard_scratch_init<<<1, 32, 0, s>>>(h->shard_scratch.p);
         k_shard_xrange<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[0].p, h->shard_scratch.p);
-        k_peer_publish_header<<<1, 32, 0, s>>>(h->state.p, h->shard_scratch.p, ctl, rank, par);
+        k_peer_publish_header<<<1, 32, 0, s>>>(h->state.p, h->shard_scratch.p, ctl, rank, par, h->peer_t0.p);
         k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagA[rank], epoch);
         mark(h, "peer_header");
         h->stats.kernel_launches += 4;
@@ -1823,10 +1837,11 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
             return fail(SDM_ERR_CAPACITY, "rank 0's tables are too small for world x cap_rows key rows");
         k_peer_root_offsets<<<1, 32, 0, s>>>(ctl, world, par, h->cap_uniq, h->cap_tris);
         CK(dev_fill(s, h->first_bits.p, 0, ((size_t) h->cap_uniq / 32 + 2) * 4));
-        CK(dev_fill(s, h->table2.p, 0xFF, (size_t) entries * 16));
-        k_peer_res_insert<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, entries - 1, h->wref.p, &ctl->status[par]);
+        k_peer_clear_table<<<h->g_light, 256, 0, s>>>(ctl, par, h->table2.p, entries);
+        k_peer_res_insert<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, entries, h->wref.p, &ctl->status[par]);
         k_peer_res_mark<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, h->wref.p, h->first_bits.p);
-        k_scan_bits_1block_dev<<<1, 1024, 0, s>>>(h->first_bits.p, h->first_prefix.p, &ctl->voff[par][world]);
+        k_peer_scan_reset<<<1, 32, 0, s>>>(h->state.p, 2);
+        k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->first_bits.p, h->first_prefix.p, 2, next_epoch(h), h->tiles.p, &ctl->voff[par][world]);
         k_peer_root_goff<<<1, 32, 0, s>>>(ctl, world, par);
         k_peer_res_pairs<<<h->g_light, 256, 0, s>>>(ctl, world, par, cap_rows, all_rows, h->table2.p, h->wref.p, h->first_bits.p, h->first_prefix.p, pairs);
         if (deliver == 0) CK(cudaStreamWaitEvent(s, h->ev_copy_done[1], 0));   // the peers are about to overwrite the set a download may still read
@@ -1840,7 +1855,8 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         if (deliver != 0 || rank == 0) CK(cudaStreamWaitEvent(s, h->ev_copy_done[1], 0));
         CK(dev_fill(s, h->tri_valid_bits.p, 0, ((size_t) h->cap_uniq / 32 + 2) * 4));
         k_peer_apply_mark<<<h->g_light, 256, 0, s>>>(ctl, rank, par, pairs, h->tri_valid_bits.p, h->vidx.p, h->peer_local.p);
-        k_scan_bits_1block_dev<<<1, 1024, 0, s>>>(h->tri_valid_bits.p, h->tri_prefix.p, &ctl->hdr[par][rank].V);
+        k_peer_scan_reset<<<1, 32, 0, s>>>(h->state.p, 3);
+        k_bitscan<<<h->g_light, 256, 0, s>>>(h->state.p, h->tri_valid_bits.p, h->tri_prefix.p, 3, next_epoch(h), h->tiles.p, &ctl->hdr[par][rank].V);
         // Rank 0 writes its rows where they belong (its second output set IS the merged mesh when deliver = 0); the other ranks compact
         // into their own second set and, for deliver = 0, push it to rank 0 in one coalesced copy.
         const bool direct = deliver == 0 && rank == 0;

@@ -48,7 +48,7 @@ struct DevState {
     uint32_t n_stragglers;      // vertices handed from k_project to k_project_tail
     uint32_t cases_from_refine; // epoch of the last k_refine that met an inexact lattice (its case indices must not be used)
     uint32_t weld_dups;         // vertices whose quantised weld key was already in the table (0: the weld merges nothing)
-    uint32_t n_active0;         // dense level of a culled scene: parents whose cells may contain the surface (k_active_parents)
+    uint32_t peer_scan_total[2];   // totals of the peer exchange's bitmap scans (unused by the host)
     uint32_t n_escaped;         // vertices whose Newton iterate left the region their inherited list is proven for (general path)
     uint32_t list_fallbacks;    // tiles of the mesh stage that had to use the cell masks instead of inherited lists
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(256) k_init_field(float* __restrict__ vox, Dev
     const uint64_t n = (uint64_t) init * init * init;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->level_count[0] = (uint32_t) (n <= cap_vox ? n : 0);
-        st->n_active0 = 0;
         if (n > cap_vox) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
     }
     if (n > cap_vox) return;
@@ -122,31 +121,6 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 // append fused in, a third of the kernel's instructions were look-back spins: ncu, profiles/).
 // k_refine_emit: surviving children are appended in the reference's order (n_id = id*8 + i*4 + j*2 + k, :51; Vec::retain
 // is stable, src/cuda/mod.rs:192) at the offset given by a block scan + decoupled look-back across tiles - a streaming pass.
-// Dense level of a culled scene: most parents lie in cells that provably contain no zero crossing - 27 equal signs, no child
-// survives (is_border, :36-49).  They get their "all outside" sign word here, and the indices of the others are gathered so that
-// k_refine works on full tiles of parents that need evaluating (with the test inside k_refine a tile of 32 consecutive cells had
-// ~5 busy lanes: 156 M warp instructions for level 0 of the 1 024-primitive scene, ncu).  The order of the gathered indices
-// does not matter: k_refine writes each parent's sign word at the parent's own index.
-__global__ void __launch_bounds__(256) k_active_parents(const float* __restrict__ in_vox, DevState* st, int level, float osx, float osy, float osz, MaskGrid grid,
-                                                        uint32_t* __restrict__ out_m27, uint32_t* __restrict__ out_idx) {
-    const uint32_t n = st->level_count[level];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nround = (n + 31u) & ~31u;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
-        bool may = false;
-        if (p < n) {
-            const float bx = in_vox[3 * (size_t) p], by = in_vox[3 * (size_t) p + 1], bz = in_vox[3 * (size_t) p + 2];
-            may = box_may_cross(grid, bx, by, bz, bx + 2.0f * osx, by + 2.0f * osy, bz + 2.0f * osz);
-            if (!may) out_m27[p] = 0u;
-        }
-        const uint32_t ball = __ballot_sync(0xffffffffu, may);
-        uint32_t base = 0;
-        if (lane == 0 && ball) base = atomicAdd(&st->n_active0, (uint32_t) __popc(ball));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (may) out_idx[base + __popc(ball & ((1u << lane) - 1u))] = p;
-    }
-}
-
 #ifndef SDM_REFINE_MINB
 #define SDM_REFINE_MINB 3
 #endif
@@ -155,12 +129,11 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
                                                 uint32_t cases_epoch /* 0: no case indices wanted */, int use_cell_flags,
                                                 const uint4* __restrict__ vl_in /* records of the previous level's parents, or null */,
                                                 const uint32_t* __restrict__ vparent_in /* record index per voxel of this level */,
-                                                uint4* __restrict__ vl_out /* one record per voxel of this level, or null */, float delta,
-                                                const uint32_t* __restrict__ active_idx /* k_active_parents' list: only these parents, or null: all */) {
+                                                uint4* __restrict__ vl_out /* one record per voxel of this level, or null */, float delta) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = active_idx ? st->n_active0 : st->level_count[level];
+    const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + 31u) >> 5;
     const bool want_cases = cases_epoch != 0u;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->ticket[TK_REFINE_EMIT] = 0;   // k_refine_emit runs after this kernel
@@ -178,7 +151,7 @@ __global__ void __launch_bounds__(256, SDM_REFINE_MINB) k_refine(const uint4* __
         const uint32_t p0 = tile << 5;
         const uint32_t np = min(32u, n - p0);
         const bool active = lane < np;
-        const uint32_t p = active ? (active_idx ? active_idx[p0 + lane] : p0 + lane) : 0u;   // this lane's parent
+        const uint32_t p = p0 + lane;   // this lane's parent
         float bx = 0.f, by = 0.f, bz = 0.f;
         if (active) {
             bx = in_vox[3 * (size_t) p + 0];
@@ -1085,18 +1058,20 @@ __global__ void __launch_bounds__(256) k_weld_mark(DevState* st, const uint32_t*
 
 // Exclusive prefix pop-count over a bit mask: word_prefix[w] = number of set bits in words [0, w).
 // which: 0 -> bits cover 3*n_tris_raw slots, total to n_verts_out; 1 -> bits cover n_tris_raw, total to n_tris_out.
+// which: 2 / 3 -> the peer exchange's bitmaps: number of bits read from *nbits_ptr (+ 64 spare bits, so that a rank look-up one
+//        word past the end is defined), total to st->peer_scan_total[which - 2]; the ticket must have been reset (k_peer_scan_reset).
 __global__ void __launch_bounds__(256) k_bitscan(DevState* st, const uint32_t* __restrict__ bits, uint32_t* __restrict__ word_prefix,
-                                                 int which, uint32_t epoch, uint64_t* tiles) {
+                                                 int which, uint32_t epoch, uint64_t* tiles, const uint32_t* nbits_ptr = nullptr) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_w[10];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nbits = which == 0 ? 3u * st->n_tris_raw : st->n_tris_raw;
+    const uint32_t nbits = which >= 2 ? *nbits_ptr + 64u : (which == 0 ? 3u * st->n_tris_raw : st->n_tris_raw);
     const uint32_t nwords = (nbits + 31u) >> 5;
     const uint32_t per_tile = blockDim.x * 4u;   // 4 consecutive words per thread
     const uint32_t ntiles = (nwords + per_tile - 1u) / per_tile;
-    uint32_t* total_out = which == 0 ? &st->n_verts_out : &st->n_tris_out;
-    const int tk = which == 0 ? TK_SCAN_FIRST : TK_SCAN_TRI;
-    const bool bad = st->error_flags != 0;
+    uint32_t* total_out = which >= 2 ? &st->peer_scan_total[which - 2] : (which == 0 ? &st->n_verts_out : &st->n_tris_out);
+    const int tk = (which & 1) == 0 ? TK_SCAN_FIRST : TK_SCAN_TRI;
+    const bool bad = which < 2 && st->error_flags != 0;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[tk], 1u);
@@ -1207,7 +1182,8 @@ __global__ void __launch_bounds__(256) k_soup(DevState* st, int level, const uin
 // the cell keeps): every shard gets the same total weight, so that no level has to be refined redundantly to find a balanced split
 // and shards in dense regions - longer primitive lists per evaluation - get fewer voxels.  bounds[0..1] = [lo, hi); the same
 // arithmetic on every rank, so the shards tile the list.
-__global__ void __launch_bounds__(1024) k_shard_bounds_by_flags(const uint8_t* __restrict__ flags, uint32_t n, uint32_t shard, uint32_t count, uint32_t* bounds) {
+__global__ void __launch_bounds__(1024) k_shard_bounds_by_flags(const uint8_t* __restrict__ flags, uint32_t n, uint32_t shard, uint32_t count, uint32_t* bounds,
+                                                                const float* __restrict__ frac /* cumulative weight fractions [count + 1], or null: equal shares */) {
     __shared__ unsigned long long s_part[1024];
     const uint32_t per = (n + 1023u) / 1024u, i0 = min(threadIdx.x * per, n), i1 = min(i0 + per, n);
     unsigned long long sum = 0;
@@ -1235,7 +1211,8 @@ __global__ void __launch_bounds__(1024) k_shard_bounds_by_flags(const uint8_t* _
     for (uint32_t b = 0; b < 2u; b++) {
         const uint32_t which = shard + b;
         if (which == 0u || which == count || total == 0ull) continue;
-        const unsigned long long target = total * which / count;
+        const unsigned long long target = frac ? min(total - 1ull, (unsigned long long) ((double) total * (double) fminf(fmaxf(frac[which], 0.0f), 1.0f)))
+                                               : total * which / count;
         if (target >= before && target < before + sum) {
             unsigned long long seen = before;
             for (uint32_t i = i0; i < i1; i++) {
@@ -1383,24 +1360,6 @@ __global__ void __launch_bounds__(1024) k_scan_bits_1block(const uint32_t* __res
     uint32_t run = s_part[threadIdx.x] - sum;
     for (uint32_t w = w0; w < w1; w++) { word_prefix[w] = run; run += __popc(bits[w]); }
 }
-// the same with the number of BITS read from device memory
-__global__ void __launch_bounds__(1024) k_scan_bits_1block_dev(const uint32_t* __restrict__ bits, uint32_t* __restrict__ word_prefix, const uint32_t* nbits) {
-    __shared__ uint32_t s_part[1024];
-    const uint32_t nwords = *nbits / 32u + 2u;
-    const uint32_t per = (nwords + 1023u) / 1024u, w0 = threadIdx.x * per, w1 = min(w0 + per, nwords);
-    uint32_t sum = 0;
-    for (uint32_t w = w0; w < w1; w++) sum += __popc(bits[w]);
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    for (uint32_t o = 1; o < 1024u; o <<= 1) {
-        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = s_part[threadIdx.x] - sum;
-    for (uint32_t w = w0; w < w1; w++) { word_prefix[w] = run; run += __popc(bits[w]); }
-}
 // pass 3: (local index, global id of the owner) for every duplicate, grouped by shard; global offset of every shard
 __global__ void __launch_bounds__(256) k_res_pairs(const uint4* __restrict__ rows, uint32_t total, const uint4* __restrict__ table, const uint32_t* __restrict__ rref,
                                                    ShardOffsets so, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
@@ -1485,6 +1444,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__global__ void k_peer_scan_reset(DevState* st, int which) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) st->ticket[(which & 1) == 0 ? TK_SCAN_FIRST : TK_SCAN_TRI] = 0;
+}
 // one block; thread i waits for flags[i] to reach `epoch`
 __global__ void k_peer_wait(const uint32_t* flags, uint32_t count, uint32_t epoch) {
     if (threadIdx.x < count) {
@@ -1495,14 +1457,49 @@ __global__ void k_peer_set_flag(uint32_t* flag, uint32_t epoch) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { __threadfence_system(); st_release_sys(flag, epoch); }
 }
 // P0: header of this rank's welded shard (scratch: k_shard_xrange's {min ordered x, max ordered x, non-finite count})
-__global__ void k_peer_publish_header(DevState* st, const uint32_t* __restrict__ scratch, PeerCtl* ctl, uint32_t rank, uint32_t parity) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_peer_mark_start(unsigned long long* t0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *t0 = global_timer_ns();
+}
+// Load balancing from measurement.  The shards' compute times of the previous step (in their headers; stable and the same for every
+// rank by the time a step starts) and the cumulative weight fractions that step used give a piecewise-constant cost density over the
+// weight axis; the new boundaries cut the cumulative cost into equal parts, half-way damped.  Every rank runs this on the same
+// inputs and gets the same fractions, so the shards still tile the list; any split gives the same mesh.
+__global__ void k_peer_rebalance(const PeerCtl* ctl, uint32_t prev_parity, uint32_t world, const float* __restrict__ frac_prev, float* __restrict__ frac_new, int have_prev) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool ok = have_prev != 0 && ctl->status[prev_parity] == 0u;
+    float t[SDM_PEER_MAX], total = 0.0f;
+    for (uint32_t r = 0; r < world; r++) {
+        t[r] = (float) ctl->hdr[prev_parity][r].pad[0];
+        ok = ok && t[r] > 0.0f && frac_prev[r + 1] > frac_prev[r];
+        total += t[r];
+    }
+    frac_new[0] = 0.0f; frac_new[world] = 1.0f;
+    if (!ok) { for (uint32_t b = 1; b < world; b++) frac_new[b] = (float) b / (float) world; return; }
+    float c0 = 0.0f;
+    uint32_t r = 0;
+    for (uint32_t b = 1; b < world; b++) {
+        const float target = total * (float) b / (float) world;
+        while (r + 1 < world && c0 + t[r] < target) { c0 += t[r]; r++; }
+        const float w = frac_prev[r] + (target - c0) / t[r] * (frac_prev[r + 1] - frac_prev[r]);
+        float f = 0.5f * frac_prev[b] + 0.5f * w;
+        f = fmaxf(f, frac_new[b - 1] + 1e-4f);
+        frac_new[b] = fminf(f, 1.0f - 1e-4f * (float) (world - b));
+    }
+}
+__global__ void k_peer_publish_header(DevState* st, const uint32_t* __restrict__ scratch, PeerCtl* ctl, uint32_t rank, uint32_t parity, const unsigned long long* t0) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     PeerHdr hd;
     hd.V = st->n_verts_out; hd.T = st->n_tris_out; hd.K = 0;
     hd.err = st->error_flags | (scratch[2] ? 0x100u : 0u) | (st->n_verts_out >= (1u << 24) ? 0x200u : 0u);   // 24-bit local indices in the key rows
     hd.min_x = ord2f((int) scratch[0]); hd.max_x = ord2f((int) scratch[1]);
     if (scratch[0] == 0x7fffffffu) { hd.min_x = 1.0f; hd.max_x = 0.0f; }   // no finite vertex
-    hd.pad[0] = hd.pad[1] = 0;
+    hd.pad[0] = (uint32_t) min((global_timer_ns() - *t0) / 1000ull, 0xFFFFFFFFull);   // this shard's compute time in microseconds (k_peer_rebalance)
+    hd.pad[1] = 0;
     ctl->hdr[parity][rank] = hd;
 }
 // P1: key rows of the welded vertices that lie inside another shard's x range (equal keys are < 1.1e-5 apart; the ranges are
@@ -1553,11 +1550,23 @@ __global__ void k_peer_root_offsets(PeerCtl* ctl, uint32_t world, uint32_t parit
     ctl->status[parity] = err;
     ctl->total_rows[parity] = k;
 }
+// rank 0's key table for one step: sized on the device from the rows that actually arrived (load factor <= 1/2)
+__device__ __forceinline__ uint32_t peer_table_size(uint32_t total_rows, uint32_t max_entries) {
+    uint32_t s = 1024;
+    while ((uint64_t) s < (uint64_t) total_rows * 2u && s < max_entries) s <<= 1;
+    return s;
+}
+__global__ void __launch_bounds__(256) k_peer_clear_table(const PeerCtl* ctl, uint32_t parity, uint4* __restrict__ table, uint32_t max_entries) {
+    const uint32_t n = peer_table_size(ctl->total_rows[parity], max_entries);
+    const uint4 empty = make_uint4(SDM_HASH_EMPTY, SDM_HASH_EMPTY, SDM_HASH_EMPTY, SDM_HASH_EMPTY);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) table[i] = empty;
+}
 // rows live in per-rank slots of cap_rows entries: row g of the flattened space is rows[g] if (g % cap_rows) < K of rank g / cap_rows
 __device__ __forceinline__ bool peer_row(const PeerCtl* ctl, uint32_t parity, uint32_t cap_rows, uint32_t g) { return (g % cap_rows) < ctl->hdr[parity][g / cap_rows].K; }
 __global__ void __launch_bounds__(256) k_peer_res_insert(const PeerCtl* ctl, uint32_t world, uint32_t parity, uint32_t cap_rows, const uint4* __restrict__ rows, uint4* table,
-                                                         uint32_t table_mask, uint32_t* __restrict__ rref, uint32_t* status) {
+                                                         uint32_t max_entries, uint32_t* __restrict__ rref, uint32_t* status) {
     if (*status) return;
+    const uint32_t table_mask = peer_table_size(ctl->total_rows[parity], max_entries) - 1u;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < world * cap_rows; g += gridDim.x * blockDim.x) {
         if (!peer_row(ctl, parity, cap_rows, g)) continue;
         const uint4 r = rows[g];
@@ -1657,8 +1666,20 @@ __global__ void __launch_bounds__(256) k_peer_push(const PeerCtl* ctl, uint32_t 
     const size_t nv = 3 * (size_t) (ctl->goff[parity][rank + 1] - ctl->goff[parity][rank]), nt = 3 * (size_t) ctl->hdr[parity][rank].T;
     const size_t ov = 3 * (size_t) ctl->goff[parity][rank], ot = 3 * (size_t) ctl->toff[parity][rank];
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = tid; i < nv; i += stride) { dst_pos[ov + i] = src_pos[i]; dst_nrm[ov + i] = src_nrm[i]; }
-    for (size_t i = tid; i < nt; i += stride) dst_idx[ot + i] = src_idx[i];
+    // 16-byte STORES (what crosses NVLink): a few head words bring the destination to a 16-byte boundary (row offsets are multiples
+    // of 12 bytes), the body gathers four source words - whatever their alignment - per store
+    auto copy = [&](const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
+        const size_t head = min(n, (size_t) ((16u - (uint32_t) (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
+        for (size_t i = tid; i < head; i += stride) dst[i] = src[i];
+        const size_t n4 = (n - head) >> 2;
+        uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst + head);
+        const uint32_t* __restrict__ sb = src + head;
+        for (size_t i = tid; i < n4; i += stride) d4[i] = make_uint4(sb[4 * i], sb[4 * i + 1], sb[4 * i + 2], sb[4 * i + 3]);
+        for (size_t i = head + (n4 << 2) + tid; i < n; i += stride) dst[i] = src[i];
+    };
+    copy(src_pos, dst_pos + ov, nv);
+    copy(src_nrm, dst_nrm + ov, nv);
+    copy(src_idx, dst_idx + ot, nt);
 }
 // totals for the host of rank 0 (and of every rank, for bookkeeping)
 __global__ void k_peer_totals(const PeerCtl* ctl, uint32_t world, uint32_t parity, PeerLocal* local) {
