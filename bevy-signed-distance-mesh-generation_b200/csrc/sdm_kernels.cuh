@@ -1292,8 +1292,11 @@ __global__ void __launch_bounds__(256) k_shard_xrange(DevState* st, const float*
     uint32_t bad = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float x = out_pos[3 * (size_t) i], y = out_pos[3 * (size_t) i + 1], z = out_pos[3 * (size_t) i + 2];
-        if (fabsf(x) <= FLT_MAX && fabsf(y) <= FLT_MAX && fabsf(z) <= FLT_MAX) { lo = min(lo, f2ord(x)); hi = max(hi, f2ord(x)); }
-        else bad++;
+        // the range is over the x every vertex's KEY stands for: x itself, 0 for NaN, the far ends for +-inf (src/cuda/mod.rs:270: NaN -> 0,
+        // `as i64` saturates) - a vertex of another shard with the same key has its x in this range whatever this vertex's y and z are
+        const float xr = (x == x) ? fminf(fmaxf(x, -FLT_MAX), FLT_MAX) : 0.0f;
+        lo = min(lo, f2ord(xr)); hi = max(hi, f2ord(xr));
+        if (!(fabsf(x) <= FLT_MAX && fabsf(y) <= FLT_MAX && fabsf(z) <= FLT_MAX)) bad++;
     }
     lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi); bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31u) == 0) {
@@ -1495,7 +1498,7 @@ __global__ void k_peer_publish_header(DevState* st, const uint32_t* __restrict__
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     PeerHdr hd;
     hd.V = st->n_verts_out; hd.T = st->n_tris_out; hd.K = 0;
-    hd.err = st->error_flags | (scratch[2] ? 0x100u : 0u) | (st->n_verts_out >= (1u << 24) ? 0x200u : 0u);   // 24-bit local indices in the key rows
+    hd.err = st->error_flags | (st->n_verts_out >= (1u << 24) ? 0x200u : 0u);   // 24-bit local indices in the key rows
     hd.min_x = ord2f((int) scratch[0]); hd.max_x = ord2f((int) scratch[1]);
     if (scratch[0] == 0x7fffffffu) { hd.min_x = 1.0f; hd.max_x = 0.0f; }   // no finite vertex
     hd.pad[0] = (uint32_t) min((global_timer_ns() - *t0) / 1000ull, 0xFFFFFFFFull);   // this shard's compute time in microseconds (k_peer_rebalance)
@@ -1518,14 +1521,13 @@ __global__ void __launch_bounds__(256) k_peer_rows(DevState* st, const float* __
     __syncthreads();
     const uint32_t n = st->n_verts_out;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float x = out_pos[3 * (size_t) i];
-        bool cand = false;
+        const float x = out_pos[3 * (size_t) i], y = out_pos[3 * (size_t) i + 1], z = out_pos[3 * (size_t) i + 2];
+        // a vertex with a non-finite coordinate is in no x range but still has a key (NaN -> 0, src/cuda/mod.rs:270): always a candidate
+        bool cand = !(fabsf(x) <= FLT_MAX && fabsf(y) <= FLT_MAX && fabsf(z) <= FLT_MAX);
         for (uint32_t q = 0; q < world; q++) cand = cand || (x >= s_lo[q] && x <= s_hi[q]);
         if (!cand) continue;
         const uint32_t slot = atomicAdd(counter, 1u);
-        if (slot < cap_rows)
-            slot_rows[slot] = make_uint4(weld_key_component(x), weld_key_component(out_pos[3 * (size_t) i + 1]), weld_key_component(out_pos[3 * (size_t) i + 2]),
-                                         (rank << 24) | i);
+        if (slot < cap_rows) slot_rows[slot] = make_uint4(weld_key_component(x), weld_key_component(y), weld_key_component(z), (rank << 24) | i);
     }
 }
 __global__ void k_peer_publish_rows(const uint32_t* counter, PeerCtl* ctl, uint32_t rank, uint32_t parity, uint32_t cap_rows) {
