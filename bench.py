@@ -257,7 +257,8 @@ def main():
               "bb_size": bb, "init_factor": init, "levels": levels, "resolution": res,
               "l2": "every step clears >0.3 GB of tables / bitmaps and rewrites all intermediates (working set > 126 MB L2); no separate flush",
               "parallelism": (f"x-slab shards of the level-{_par.choose_split_level(init, levels, max(world, args.gpus), _par.scene_is_culled(scene))} active list over {max(world, args.gpus)} GPU(s), "
-                              "welded where they are made, interface keys resolved and shards assembled on rank 0 (NCCL)") if max(world, args.gpus) > 1 else "1 GPU"}
+                              "welded where they are made, interface keys resolved on rank 0, rows pushed into rank 0's HBM over NVLink through peer-mapped memory "
+                              "(device-side flags; --exchange nccl: the host-driven NCCL exchange)") if max(world, args.gpus) > 1 else "1 GPU"}
 
     if args.impl == "reference":
         if rank != 0:

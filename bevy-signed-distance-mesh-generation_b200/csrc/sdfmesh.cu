@@ -1763,6 +1763,15 @@ int sdm_peer_attach(SdmHandle* h, const SdmPeerExport* root, uint32_t rank, uint
     return SDM_OK;
 }
 
+int sdm_peer_detach(SdmHandle* h) {
+    if (!h) return fail(SDM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (void*& m : h->ipc_mapped) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    h->ctl = nullptr; h->peer_rows = nullptr; h->peer_pairs = nullptr; h->root_pos = h->root_nrm = nullptr; h->root_idx = nullptr;
+    return SDM_OK;
+}
+
 int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, uint32_t epoch, int deliver, uint32_t phase_mask, int spin) {
     if (!h) return fail(SDM_ERR_INVALID, "null handle");
     if (!h->ctl) return fail(SDM_ERR_STATE, "sdm_peer_attach first");
@@ -1822,7 +1831,7 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
     }
     if (phase_mask & 2u) {   // P1: key rows of the vertices inside another shard's x range -> this rank's slot on rank 0
         NvtxRange nv(h, "peer P1: interface key rows");
-        if (spin) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagA, world, epoch);
+        if (spin) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagA, world, epoch, h->state.p);
         k_peer_rows<<<h->g_light, 256, 0, s>>>(h->state.p, h->out_pos[0].p, ctl, rank, world, par, my_rows, cap_rows, counter);
         k_peer_publish_rows<<<1, 32, 0, s>>>(counter, ctl, rank, par, cap_rows);
         k_peer_set_flag<<<1, 32, 0, s>>>(&ctl->flagB[rank], epoch);
@@ -1831,7 +1840,7 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
     }
     if ((phase_mask & 4u) && rank == 0) {   // P2: owners, removal bitmap, offsets, pairs
         NvtxRange nv(h, "peer P2: resolve");
-        if (spin) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagB, world, epoch);
+        if (spin) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagB, world, epoch, h->state.p);
         const uint32_t entries = std::min<uint32_t>(pow2_at_least(std::max<uint64_t>((uint64_t) world * cap_rows * 2, 1024)), h->table_entries);
         if ((uint64_t) entries * 4 < (uint64_t) world * cap_rows * 5 || (uint64_t) world * cap_rows > h->wref.n)
             return fail(SDM_ERR_CAPACITY, "rank 0's tables are too small for world x cap_rows key rows");
@@ -1851,7 +1860,7 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
     }
     if (phase_mask & 8u) {   // P3: drop own duplicates, global indices, rows to their final place
         NvtxRange nv(h, "peer P3: apply + deliver");
-        if (spin) k_peer_wait<<<1, 32, 0, s>>>(&ctl->flagC, 1, epoch);
+        if (spin) k_peer_wait<<<1, 32, 0, s>>>(&ctl->flagC, 1, epoch, h->state.p);
         if (deliver != 0 || rank == 0) CK(cudaStreamWaitEvent(s, h->ev_copy_done[1], 0));
         CK(dev_fill(s, h->tri_valid_bits.p, 0, ((size_t) h->cap_uniq / 32 + 2) * 4));
         k_peer_apply_mark<<<h->g_light, 256, 0, s>>>(ctl, rank, par, pairs, h->tri_valid_bits.p, h->vidx.p, h->peer_local.p);
@@ -1875,7 +1884,7 @@ int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, u
         h->stats.kernel_launches += 6 + (spin ? 1 : 0);
     }
     if (phase_mask & 16u) {   // P4: rank 0 waits for everybody's rows; totals for the host
-        if (spin && rank == 0) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagD, world, epoch);
+        if (spin && rank == 0) k_peer_wait<<<1, 32, 0, s>>>(ctl->flagD, world, epoch, h->state.p);
         k_peer_totals<<<1, 32, 0, s>>>(ctl, world, par, h->peer_local.p);
         CK(cudaEventRecord(h->ev1, s));
         CK(cudaEventRecord(h->ev_mesh_done[1], s));

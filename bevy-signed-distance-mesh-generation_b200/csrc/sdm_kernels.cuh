@@ -15,7 +15,8 @@
 //                     finite filter (src/cuda/mod.rs:289), first-occurrence slot per vertex
 //   k_weld_keys / k_weld_min / k_weld_mark / k_bitscan / k_emit_*   the reference-order weld (src/cuda/mod.rs:263-296)
 //   k_soup            the reference's raw 5-slot Triangle format (compute_mesh_generation.cu:107-118)
-//   k_shard_* / k_res_* / k_fix_*   multi-GPU: shard selection, distributed weld
+//   k_shard_* / k_res_* / k_fix_*   multi-GPU: shard selection, host-driven distributed weld
+//   k_peer_*          multi-GPU: the same weld driven from the device over peer-mapped memory (flags, key rows, pairs, pushes)
 //
 // All kernels read their problem sizes from DevState in device memory, so that a whole remesh is enqueued without any host
 // synchronisation.  A kernel that evaluates the SDF never waits for another block: every ordered step (compaction, offsets,
@@ -34,6 +35,7 @@ namespace cg = cooperative_groups;
 enum Ticket : int { TK_REFINE0 = 0, TK_CLASSIFY = 16, TK_PROJECT = 17, TK_SCAN_FIRST = 18, TK_SCAN_TRI = 19, TK_TAIL = 20, TK_ASSIGN = 21, TK_REFINE_EMIT = 22, TK_NORMALS = 23, TK_ORIENT = 24, TK_EDGES = 25, TK_COUNT = 26 };
 enum ErrFlag : uint32_t {
     ERR_VOXEL_CAP = 1u, ERR_TRI_CAP = 2u, ERR_UNIQ_CAP = 4u, ERR_HASH_FULL = 8u,
+    ERR_PEER_TIMEOUT = 32u,   // peer exchange: a flag from another rank did not arrive within 20 s
     ERR_LATTICE = 16u   // a voxel is not on the integer lattice the fast vertex keys assume: the host retries with the generic keys
 };
 
@@ -297,15 +299,12 @@ __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ i
 //                  k_refine already wrote the case indices from its lattice signs
 //   k_tri_offsets  triangle count per voxel from the case table, exclusive scan in list order -> tri_off, n_tris_raw
 //   k_edges        every edge the case uses gets its mid-point mix(a, b, 0.5f) (marching_cubes.cu:13-16), de-duplicated
-//                  across voxels by the exact bit pattern of the mid-point in a 128-bit-CAS hash table: an identical
+//                  across voxels by the exact start point in a hash table (see "Fast vertex keys" below): an identical
 //                  start point gives an identical projection, normal and weld key, so it is projected once instead of
 //                  once per incident triangle (~6x); mid-points that differ in any bit stay separate and are merged - if
 //                  at all - by the reference's quantised weld later, exactly as the reference would.
-//                  slot_ref[3*triangle + corner] = hash entry of that corner's vertex; won[v] = edges whose entry this
-//                  voxel created
-//   k_assign_uids  scan of popc(won) in list order -> vertex ids (consecutive ids are spatial neighbours: this keeps the
-//                  later per-vertex kernels' primitive lists short and their loads coalesced); writes the start points
-//                  and the id into the winner's hash entry.
+//                  slot_ref[3*triangle + corner] = table entry of that corner's vertex; the vertices a tile of 256 voxels
+//                  created get consecutive ids, their start points and the list record of the creating voxel.
 __device__ __forceinline__ void mc_edge_corners(int e, int& c0, int& c1) {   // MC_EDGE_TABLE (marching_cubes_constants.cu:3-16)
     c0 = (e < 4) ? ((e == 3) ? 0 : e) : (e < 8 ? ((e == 7) ? 4 : e) : e - 8);
     c1 = (e < 4) ? ((e == 3) ? 3 : e + 1) : (e < 8 ? ((e == 7) ? 7 : e + 1) : e - 4);
@@ -1450,10 +1449,21 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void k_peer_scan_reset(DevState* st, int which) {
     if (threadIdx.x == 0 && blockIdx.x == 0) st->ticket[(which & 1) == 0 ? TK_SCAN_FIRST : TK_SCAN_TRI] = 0;
 }
-// one block; thread i waits for flags[i] to reach `epoch`
-__global__ void k_peer_wait(const uint32_t* flags, uint32_t count, uint32_t epoch) {
+// one block; thread i waits for flags[i] to reach `epoch`.  A peer that never arrives (its process died) must not hang this GPU:
+// after 20 s the waiter gives up and marks the step failed.
+__global__ void k_peer_wait(const uint32_t* flags, uint32_t count, uint32_t epoch, DevState* st) {
     if (threadIdx.x < count) {
-        while ((int32_t) (ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(200);
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        while ((int32_t) (ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            __nanosleep(200);
+            if ((++spins & 0xFFFu) == 0u) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 20000000000ull) { atomicOr(&st->error_flags, ERR_PEER_TIMEOUT); break; }
+            }
+        }
     }
 }
 __global__ void k_peer_set_flag(uint32_t* flag, uint32_t epoch) {

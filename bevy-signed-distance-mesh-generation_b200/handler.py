@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "sdm_shard_remesh", "sdm_shard_buffers", "sdm_shard_prepare_send", "sdm_shard_reserve", "sdm_shard_weld",
     "sdm_shard_local_weld", "sdm_shard_boundary_keys", "sdm_shard_key_scratch", "sdm_shard_resolve", "sdm_shard_fixup",
     "sdm_shard_welded_buffers", "sdm_shard_reserve_welded",
-    "sdm_mesh_save_obj", "sdm_hash_bytes", "sdm_reserve", "sdm_peer_root_export", "sdm_peer_attach", "sdm_peer_step", "sdm_peer_finish",
+    "sdm_mesh_save_obj", "sdm_hash_bytes", "sdm_reserve", "sdm_peer_root_export", "sdm_peer_attach", "sdm_peer_detach", "sdm_peer_step", "sdm_peer_finish",
     "sdm_peer_download_async", "sdm_render",
     "sdm_get_stats", "sdm_set_profiling", "sdm_get_kernel_times", "sdm_debug_fetch", "sdm_selftest_math", "sdm_mesh_download_async", "sdm_mesh_download_wait",
 ]
@@ -445,6 +445,9 @@ class CudaHandler:
         e = _PeerExport.from_buffer_copy(export)
         root = same_process_root._h if same_process_root is not None else None
         self._check(self._lib.sdm_peer_attach(self._h, ctypes.byref(e), ctypes.c_uint32(rank), ctypes.c_uint32(world), root))
+
+    def peer_detach(self) -> None:
+        self._check(self._lib.sdm_peer_detach(self._h))
 
     def peer_step(self, bb_size, init_factor, levels, split_level, epoch, deliver=0, phase_mask=31, spin=True) -> None:
         p = _params(bb_size, init_factor, levels)

@@ -153,31 +153,56 @@ class PeerRemesher:
         self.last_gpu_ms = 0.0
         self.mesh = None
         self.last = None
-        dev = torch.device("cuda", torch.cuda.current_device())
-        # sizes, through the host-driven calls (once)
-        h = self.h
-        h.shard_remesh(bb_size, init_factor, levels, self.split_level, rank, world)
+        self._dev = torch.device("cuda", torch.cuda.current_device())
+        self.shared = None
+        self.growth = 1.0
+        self._setup()
+
+    def _setup(self):
+        """Sizes through the host-driven calls (once, or again with more head room after a step that did not fit), capacities,
+        rank 0's export, everybody's attach."""
+        import torch
+
+        h, dist, rank, world = self.h, self.dist, self.rank, self.world
+        info = h.shard_remesh(self.bb, self.init, self.levels, self.split_level, rank, world)
         w = h.shard_local_weld()
-        mine = torch.tensor([w["vertices"], w["triangles"]], dtype=torch.int64, device=dev)
-        allc = torch.empty((world, 2), dtype=torch.int64, device=dev)
+        mine = torch.tensor([w["vertices"], w["triangles"]], dtype=torch.int64, device=self._dev)
+        allc = torch.empty((world, 2), dtype=torch.int64, device=self._dev)
         dist.all_gather_into_tensor(allc, mine)
         totals = allc.sum(dim=0).cpu().tolist()
         # (wandering Newton iterates can stretch a shard's x range over the whole domain - Mandelbulb - and then every vertex of the
         # other shards is an interface candidate: a slot must hold the largest shard)
-        self.cap_vox, self.cap_rows = peer_capacities(int(totals[0]), int(totals[1]), world, int(allc[:, 0].max().item()))
+        self.cap_vox, self.cap_rows = peer_capacities(int(totals[0]), int(totals[1]), world, int(allc[:, 0].max().item() * self.growth * 1.5))
+        # every rank: head room for a shard that the measured load balancing makes larger than the even split's
+        h.reserve(max(int(max(info["final_voxels"], w["vertices"] / 2.0, w["triangles"] / 3.0) * 1.6 * self.growth) + 4096, self.init ** 3))
         if rank == 0:
-            h.reserve(self.cap_vox)
+            h.reserve(int(self.cap_vox * self.growth))
         blob = [h.peer_root_export(world, self.cap_rows) if rank == 0 else None]
         dist.broadcast_object_list(blob, src=0)
         h.peer_attach(blob[0], rank, world)
         torch.cuda.synchronize()
         dist.barrier()
-        self.shared = None
+
+    def _recover(self):
+        """A step failed on all ranks alike (a shard, the merged mesh or a key-row slot did not fit): unmap, grow, set up again."""
+        self.h.peer_detach()
+        self.dist.barrier()
+        self.growth *= 1.5
+        self._setup()
 
     def step(self, deliver=0):
-        self.epoch += 1
-        self.h.peer_step(self.bb, self.init, self.levels, self.split_level, self.epoch, deliver, 31, True)
-        res, m = self.h.peer_finish()
+        from .handler import SdfMeshError
+
+        for attempt in range(3):
+            self.epoch += 1
+            self.h.peer_step(self.bb, self.init, self.levels, self.split_level, self.epoch, deliver, 31, True)
+            try:
+                res, m = self.h.peer_finish()
+                break
+            except SdfMeshError as exc:        # every rank sees the same status word, so all of them take this branch together
+                if exc.code != 4 or attempt == 2:
+                    raise
+                self._recover()
         self.last, self.mesh = res, (m if (deliver == 0 and self.rank == 0) else None)
         self.last_gpu_ms = res["gpu_ms"]
         return {"triangles": int(res["total_triangles"]), "vertices": int(res["total_vertices"])}

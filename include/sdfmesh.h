@@ -276,6 +276,8 @@ int sdm_peer_root_export(SdmHandle* h, uint32_t world, uint32_t cap_rows_per_ran
 /* every rank (rank 0 too).  same_process_root != NULL: ranks emulated by several handles of one process (tests): rank 0's pointers are
  * used directly, and the caller must issue the phases of a step one by one (phase_mask) with a synchronisation in between. */
 int sdm_peer_attach(SdmHandle* h, const SdmPeerExport* root, uint32_t rank, uint32_t world, SdmHandle* same_process_root);
+/* Unmaps rank 0's memory (before rank 0 grows its buffers and exports again after a step that did not fit). */
+int sdm_peer_detach(SdmHandle* h);
 /* phase_mask: bit p = enqueue phase p (0..4); spin != 0: each phase first waits on the device for the flags it depends on
  * (one rank per GPU only).  epoch: 1, 2, 3, ... the same on all ranks. */
 int sdm_peer_step(SdmHandle* h, const SdmParams* params, uint32_t split_level, uint32_t epoch, int deliver, uint32_t phase_mask, int spin);
