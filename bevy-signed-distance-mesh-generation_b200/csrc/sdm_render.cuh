@@ -62,10 +62,9 @@ __device__ __forceinline__ F3 aces_tone(F3 h) {
     return f3(sat(r.x), sat(r.y), sat(r.z));
 }
 
-__global__ void __launch_bounds__(128) k_render(const uint4* __restrict__ scene, uchar4* __restrict__ out, RenderGlobals g, RenderCamera cam, uint32_t tex_w,
-                                               uint32_t tex_h, MaskGrid grid) {
-    extern __shared__ uint4 smem[];
-    const SceneView sc = stage_scene_masked(scene, smem, grid);
+// one pixel per lane; shared by the library kernel (k_render) and the reference-ABI module (csrc/compat_render.cu)
+__device__ __forceinline__ void render_pixel(const SceneView& sc, const MaskGrid& grid, uchar4* __restrict__ out, const RenderGlobals& g, const RenderCamera& cam,
+                                             uint32_t tex_w, uint32_t tex_h) {
     // render_texture_coord (common.cu:186-215): 4 x 8 pixels per warp, 2 x 2 warps per block, blocks row-major over width / 8 columns
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bcx = (int) tex_w / 8;
@@ -128,6 +127,13 @@ __global__ void __launch_bounds__(128) k_render(const uint4* __restrict__ scene,
     // index_2d (common.cu:32-35)
     const uint32_t idx = (uint32_t) min(max(tx, 0), (int) tex_w - 1) + (uint32_t) min(max(ty, 0), (int) tex_h - 1) * tex_w;
     out[idx] = make_uchar4((unsigned char) (clamp01(color.x) * 255.0f), (unsigned char) (clamp01(color.y) * 255.0f), (unsigned char) (clamp01(color.z) * 255.0f), 0xFF);
+}
+
+__global__ void __launch_bounds__(128) k_render(const uint4* __restrict__ scene, uchar4* __restrict__ out, RenderGlobals g, RenderCamera cam, uint32_t tex_w,
+                                               uint32_t tex_h, MaskGrid grid) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    render_pixel(sc, grid, out, g, cam, tex_w, tex_h);
 }
 
 }  // namespace sdm

@@ -99,3 +99,48 @@ def test_reference_abi_module_matches_oracle(oracle_mod):
     d.d2h(tris, d_tri)
     want, _ = o.mesh_raw(vox, vs)
     assert np.array_equal(bits(tris), bits(want)), "triangle soup differs"
+
+
+class RenderTexture(ctypes.Structure):   # bindings.h:38-41
+    _fields_ = [("size", ctypes.c_uint * 2), ("data", ctypes.c_uint64)]
+
+
+def test_reference_abi_render_module(handler):
+    """compat/compute_render.ptx: the reference's `compute_render` symbol with its by-value RenderTexture / GlobalsBuffer / CameraBuffer
+    parameters, loaded and launched the way cudarc does (src/cuda/mod.rs:70-79, 372-399: grid = w * h / 128, block = 128).  Same bytes as
+    sdm_render on the reference's scene (which tests/test_gpu_render.py pins to the reference kernel itself)."""
+    from bsdmg_b200 import handler as H
+
+    ptx = PTX.parent / "compute_render.ptx"
+    assert ptx.exists(), "run __graft_entry__.build()"
+    assert ".visible .entry compute_render(" in ptx.read_text()
+    d = Driver.__new__(Driver)
+    d.cu = ctypes.CDLL("libcuda.so.1")
+    d.ck(d.cu.cuInit(0))
+    dev = ctypes.c_int()
+    d.ck(d.cu.cuDeviceGet(ctypes.byref(dev), 0))
+    d.ctx = ctypes.c_void_p()
+    d.ck(d.cu.cuDevicePrimaryCtxRetain(ctypes.byref(d.ctx), dev))
+    d.ck(d.cu.cuCtxSetCurrent(d.ctx))
+    d.mod = ctypes.c_void_p()
+    d.ck(d.cu.cuModuleLoadData(ctypes.byref(d.mod), ptx.read_bytes() + b"\0"))
+    f = d.func("compute_render")
+    w, h = 256, 144
+    pos, fwd = (6.0, 3.0, 7.0), np.array([-6.0, -3.0, -7.0]) / np.linalg.norm([6.0, 3.0, 7.0])
+    right = np.cross(fwd, [0.0, 1.0, 0.0]); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    f32 = lambda v: [float(np.float32(x)) for x in v]
+    g = H._RenderGlobals(7, 1.5, (ctypes.c_uint * 2)(w, h), (ctypes.c_float * 2)(float(w), float(h)))
+    c = H._RenderCamera((ctypes.c_float * 3)(*f32(pos)), (ctypes.c_float * 3)(*f32(fwd)), (ctypes.c_float * 3)(*f32(up)), (ctypes.c_float * 3)(*f32(right)),
+                        float(np.float32(0.9)))
+    d_img = d.alloc(w * h * 4)
+    tex = RenderTexture((ctypes.c_uint * 2)(w, h), d_img.value)
+    argv = (ctypes.c_void_p * 3)(*[ctypes.cast(ctypes.byref(p), ctypes.c_void_p) for p in (tex, g, c)])
+    d.ck(d.cu.cuLaunchKernel(f, (w * h) // 128, 1, 1, 128, 1, 1, 0, None, argv, None))
+    d.ck(d.cu.cuCtxSynchronize())
+    got = np.empty((h, w, 4), np.uint8)
+    d.d2h(got, d_img)
+    handler.set_scene(scenes.render_scene())
+    want = handler.render(w, h, f32(pos), f32(fwd), f32(up), f32(right), float(np.float32(0.9)), tick=7, time=1.5)
+    assert len(np.unique(want.reshape(-1, 4), axis=0)) > 50
+    assert np.array_equal(got, want)
