@@ -400,6 +400,10 @@ __global__ void __launch_bounds__(256) k_tri_offsets(DevState* st, int level, co
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef SDM_PREFETCH
+#define SDM_PREFETCH 1   /* next chunk / tile on its way to L1 while the current one is evaluated: k_project 3.25 -> 3.13 ms on configs[2] */
+#endif
 
 // Fast vertex keys.  On a dyadic grid (the default 5 / 2^k one, any grid whose coordinates are exact multiples of half a voxel)
 // an edge mid-point is identified by three integers, its coordinates in units of half a voxel, so a table entry is ONE 64-bit
@@ -717,6 +721,11 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_project(const uint4* __r
                 len = __shfl_sync(0xffffffffu, len, 0);
                 if (base >= n) { drained = true; break; }
                 chunk_next = base; chunk_end = min(base + len, n);
+#if SDM_PREFETCH
+                // the chunk's start points and record indices on their way to L1 (32 entries = one 128-byte line of indices)
+                if (base + lane * 32u < chunk_end) { if (lists) prefetch_l1(urec + base + lane * 32u); }
+                if (3u * base + lane * 32u < 3u * chunk_end) prefetch_l1(ustart + 3 * (size_t) base + lane * 32u);
+#endif
             }
             const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
             if (!have && idx < chunk_end) {
@@ -881,7 +890,7 @@ __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* _
 // DRAM access per vertex that is free while the SM is busy with the twelve evaluations (as a kernel of its own it took a
 // third of this kernel's time doing nothing but waiting for memory).
 #ifndef SDM_NRM_MINB
-#define SDM_NRM_MINB 6
+#define SDM_NRM_MINB 5   /* 96 registers: 1.35 -> 1.22 ms on configs[2] (6 blocks = 80 registers spilled the per-lane test's state) */
 #endif
 __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
                                                         float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
@@ -916,6 +925,12 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
         if (u0 >= n) { if (gk == 0) break; gk = group - 1; continue; }
         const uint32_t u = u0 + lane;
         const bool active = u < n;
+#if SDM_PREFETCH
+        if (gk + 1 < group && u0 + 32u < n) {   // the next tile of this group
+            if (lane < 3u) prefetch_l1(upos + 3 * (size_t) (u0 + 32u) + lane * 32u);
+            else if (lane == 3u && lists) prefetch_l1(urec + u0 + 32u);
+        }
+#endif
         float x = 0.f, y = 0.f, z = 0.f;
         if (active) { x = upos[3 * (size_t) u]; y = upos[3 * (size_t) u + 1]; z = upos[3 * (size_t) u + 2]; }
         if (weld_table && active) wref[u] = weld_insert_key(st, upos, u, weld_table, table_mask);
@@ -968,6 +983,12 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
         const uint32_t t0 = g0 + 32u * gk;
         if (t0 >= T) { if (gk == 0) break; gk = group - 1; continue; }
         const uint32_t t = t0 + lane;
+#if SDM_PREFETCH
+        if (gk + 1 < group && t0 + 32u < T) {   // the next tile of this group: its table references and records
+            if (lane < 3u) prefetch_l1(slot_ref + 3 * (size_t) (t0 + 32u) + lane * 32u);
+            else if (lane == 3u && lists) prefetch_l1(tri_rec + t0 + 32u);
+        }
+#endif
         bool valid = false;
         uint32_t u[3] = { 0, 0, 0 };
         float v[3][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
