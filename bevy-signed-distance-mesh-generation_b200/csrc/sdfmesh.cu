@@ -1958,6 +1958,8 @@ int sdm_debug_fetch(SdmHandle* h, const char* name, void* dst, size_t bytes) {
     else if (n == "first_slot") { src = h->first_slot.p; have = h->first_slot.n * 4; }
     else if (n == "masks_fine") { src = h->masks_fine.p; have = h->masks_fine.n * 4; }
     else if (n == "masks_coarse") { src = h->masks_coarse.p; have = h->masks_coarse.n * 4; }
+    else if (n == "state") { src = h->state.p; have = sizeof(DevState); }
+    else if (n == "stragglers") { src = h->stragglers.p; have = h->stragglers.n * sizeof(Straggler); }
     else return fail(SDM_ERR_INVALID, "unknown buffer name");
     if (bytes > have) return fail(SDM_ERR_INVALID, "buffer smaller than requested");
     CK(cudaStreamSynchronize(h->stream));

@@ -55,6 +55,7 @@ struct DevState {
     uint32_t list_fallbacks;    // tiles of the mesh stage that had to use the cell masks instead of inherited lists
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
+    unsigned long long tail_steps, tail_rebuilds, tail_unlisted;   // k_project_tail: warp steps, list rebuilds, steps without a tile list (sdm_debug_fetch "state")
 };
 
 // Marching-cubes tables staged per block
@@ -634,7 +635,7 @@ __global__ void k_reset_mesh_state(DevState* st) {
     st->n_tris_raw = 0; st->n_uniq = 0; st->n_tris_out = 0; st->n_verts_out = 0;
     for (int i = TK_CLASSIFY; i < TK_COUNT; i++) st->ticket[i] = 0;
     st->n_stragglers = 0; st->weld_dups = 0;
-    st->newton_iters = 0;
+    st->newton_iters = 0; st->tail_steps = 0; st->tail_rebuilds = 0; st->tail_unlisted = 0;
     st->n_escaped = 0; st->list_fallbacks = 0;
     for (int i = WK_CLASSIFY; i < 6; i++) st->prim_evals[i] = 0;   // refine's counter is reset with the field
 }
@@ -798,6 +799,7 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
     const uint32_t half = lane >> 4;
     const uint32_t n = min(st->n_stragglers, cap_stragglers);
     unsigned long long extra_iters = 0, work = 0;
+    uint32_t dbg_steps = 0, dbg_rebuilds = 0, dbg_unlisted = 0;
     while (true) {
         uint32_t idx0 = 0;
         if (lane == 0) idx0 = atomicAdd(&st->ticket[TK_TAIL], 2u);
@@ -823,15 +825,29 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
         uint32_t recent = 0, since = 0;
         float lcx = gx, lcy = gy, lcz = gz;
         bool list_valid = false;
-        while (__any_sync(0xffffffffu, running)) {
+        uint32_t listed_for = 0;   // the halves the current list was built for
+        while (true) {
+            const uint32_t run_mask = __ballot_sync(0xffffffffu, running);
+            if (!run_mask) break;
+            // a half that has finished must not leave its primitives in the other's list (a vertex that went NaN outside the mask
+            // grid left the whole table there: 1 400 steps of its partner at 106 us each - the 171 ms frame of the animated run)
+            if (run_mask != listed_for) list_valid = false;
             const float mvx = gx - lcx, mvy = gy - lcy, mvz = gz - lcz;
             const bool moved = running && !(mvx * mvx + mvy * mvy + mvz * mvz <= (0.5f * slack) * (0.5f * slack));   // NaN -> rebuild
             if (!list_valid || __any_sync(0xffffffffu, moved)) {
                 if (list_valid && ++recent >= 4u && slack < max_slack) { slack = fminf(2.0f * slack, max_slack); recent = 0; }
+                listed_for = run_mask;
+#ifdef SDM_TAIL_SERIAL_REFINE
                 tile_mask_from_point(grid, sc, running && hl == 0, gx, gy, gz, slack);
+#else
+                tile_mask_from_half_points(grid, sc, running, gx, gy, gz, slack);
+#endif
                 lcx = gx; lcy = gy; lcz = gz;
                 list_valid = true;
+                dbg_rebuilds++;
             }
+            dbg_steps++;
+            if (sc.wmask && *sc.tcount == SDM_TLIST_NONE) dbg_unlisted++;
             if (++since >= 64u) { since = 0; recent >>= 1; }   // rebuilds far apart do not add up
             if (lane == 0) work += (unsigned long long) tile_prims(sc) * 13u * (uint32_t) __popc(__ballot_sync(0xffffffffu, running && hl == 0));
             else (void) __ballot_sync(0xffffffffu, running && hl == 0);
@@ -870,6 +886,10 @@ __global__ void __launch_bounds__(128) k_project_tail(const uint4* __restrict__ 
     extra_iters += __shfl_xor_sync(0xffffffffu, extra_iters, 16);
     if (lane == 0 && extra_iters) atomicAdd(&st->newton_iters, extra_iters);
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_TAIL], work);
+    if (lane == 0 && dbg_steps) {
+        atomicAdd(&st->tail_steps, (unsigned long long) dbg_steps); atomicAdd(&st->tail_rebuilds, (unsigned long long) dbg_rebuilds);
+        atomicAdd(&st->tail_unlisted, (unsigned long long) dbg_unlisted);
+    }
 }
 
 __device__ __forceinline__ uint32_t tile_group(uint32_t ntiles, uint32_t warps) { return max(1u, min(8u, ntiles / (warps * 4u))); }

@@ -130,13 +130,16 @@ def test_many1024_remesh_matches_reference_kernels(refgpu, handler, oracle_mod, 
     assert np.array_equal(bits(mesh.positions), bits(pos)) and np.array_equal(bits(mesh.normals), bits(nrm))
 
 
-def test_c3_fullsize_matches_reference_kernels(refgpu, handler, oracle_mod):
-    """BASELINE configs[2] at its full size - 1024 primitives, INIT 64 x 4 levels = 1024^3, the configuration bench.py quotes:
+@pytest.mark.parametrize("t", [None, pytest.param(254 / 60.0, marks=_SLOW)])
+def test_c3_fullsize_matches_reference_kernels(refgpu, handler, oracle_mod, t):
+    """(t = 254/60: the frame of the animated run, configs[4], whose Newton orbit leaves the mask grid - the tail kernel's
+    mask-level refinement; minutes in the reference kernel.)
+    BASELINE configs[2] at its full size - 1024 primitives, INIT 64 x 4 levels = 1024^3, the configuration bench.py quotes:
     the active list of every level, every per-voxel case and all 42 M triangle slots (positions and normals, post-flip) are
     compared BYTE FOR BYTE with the reference's two kernels run un-culled on the same GPU (functor template over the
     reference's own sd_box / sd_line / smooth_min, IEEE flags); the welded mesh is compared with the reference host's weld
     (src/cuda/mod.rs:263-296, restated in oracle/sdm_oracle.cpp) of that soup."""
-    table = scenes.many_primitives(1024)
+    table = scenes.many_primitives(1024) if t is None else scenes.many_primitives(1024, t=t)
     handler.set_scene(table)
     lists, vs = _ref_descent(refgpu, table, 5.0, 64, 4, oracle_mod)
     handler.field_reset(5.0, 64)
