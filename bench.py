@@ -345,6 +345,10 @@ def main():
             ktimes.setdefault(name, []).append(ms)
     h.set_profiling(False)
     st = h.stats()
+    try:   # DevState word 55: triangles the six-sample orientation test left to the twelve-sample pass (this rank's shard)
+        orient_pending = int(h.debug_fetch("state", 76, np.uint32)[55])
+    except Exception:
+        orient_pending = None
     kavg = {k: (sum(v) / reps) for k, v in ktimes.items()}           # ms per step, summed over the launches of that name
     step_sum = sum(kavg.values())
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
@@ -416,6 +420,7 @@ def main():
             "level_counts": st["level_counts"][: levels + 1], "prim_point_evals_per_step": st["prim_evals"], "gpu_launches": launches, "clocks": clocks,
             "newton": {"iterations": st["newton_iterations"], "stragglers": st["stragglers"], "escaped_vertices": st["escaped_vertices"],
                        "list_fallback_tiles": st["list_fallback_tiles"]},
+            "orient_pending_triangles": orient_pending,
             "e2e": {"value": float(res) ** 3 * args.steps / e2e["elapsed"], "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["elapsed"] * 1e3 / args.steps},
             "kernel_ms": {k: round(v, 5) for k, v in kavg.items()},

@@ -125,7 +125,7 @@ DevPrim make_capsule(H3 b0, H3 b1, float lw, uint32_t fold, float k) {
     return d;
 }
 
-int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>& blob, bool* has_mandelbulb) {
+int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>& blob, bool* has_mandelbulb, float* reach) {
     std::vector<DevPrim> dp;
     *has_mandelbulb = false;
     for (uint32_t i = 0; i < count; i++) {
@@ -194,6 +194,17 @@ int compile_scene(const SdmPrimitive* prims, uint32_t count, std::vector<uint4>&
     blob.assign(bytes / 16, make_uint4(0, 0, 0, 0));
     float kmax = 0.0f;
     for (const DevPrim& q : dp) if (q.fold == SDM_FOLD_SMOOTH_MIN) kmax = std::max(kmax, q.k);
+    // bound on |d_i(p)| - |p|_1 over the table (k_orient<true>'s rounding bound): |centre| + extent, plus what a smooth-min step can subtract
+    double far = 0.0;
+    for (const DevPrim& q : dp) {
+        const double c = std::fabs((double) q.v0[0]) + std::fabs((double) q.v0[1]) + std::fabs((double) q.v0[2]);
+        double ext = 0.0;
+        if (q.kind == SDM_PRIM_SPHERE) ext = std::fabs((double) q.s0);
+        else if (q.kind == SDM_PRIM_CAPSULE) ext = std::fabs((double) q.s0) + std::fabs((double) q.s1);
+        else if (q.kind == SDM_PRIM_BOX) ext = std::fabs((double) q.v1[0]) + std::fabs((double) q.v1[1]) + std::fabs((double) q.v1[2]);
+        far = std::max(far, c + ext);
+    }
+    *reach = (float) (far * 1.001 + (double) kmax + 1.0);   // NaN / inf parameters: the six-sample test then decides nothing
     SceneHeader hdr { (uint32_t) dp.size(), (uint32_t) runs.size(), (uint32_t) bytes, kmax };
     memcpy(blob.data(), &hdr, 16);
     if (!runs.empty()) memcpy(blob.data() + 1, runs.data(), runs.size() * sizeof(DevRun));
@@ -214,6 +225,8 @@ struct SdmHandle {
     uint32_t scene_bytes = 0;
     uint32_t scene_nprims = 0;          // compiled primitives (skeletons expanded)
     bool mask_capable = false;          // large scene of 1-Lipschitz primitives: per-cell primitive masks are used
+    bool lipschitz = false;             // no Mandelbulb estimator in the table
+    float scene_reach = 0.0f;           // max over the table of |centre|_1 + extent (+ kmax + 1), see k_orient<true>
     DevBuf<uint32_t> masks_fine, masks_coarse;
     DevBuf<uint8_t> cell_maybe;         // per fine cell: 0 = provably no zero crossing inside (k_build_masks)
     MaskGrid grid {};                   // grid.enabled == 0 until ensure_masks has built it
@@ -250,6 +263,7 @@ struct SdmHandle {
     uint32_t field_init = 0, lat_fail_init = 0;
     DevBuf<uint32_t> vidx;             // per vertex: its index in the welded output
     DevBuf<uint32_t> tri_off, slot_ref, tri_uid, first_slot, wref, first_bits, first_prefix, tri_valid_bits, tri_prefix;
+    DevBuf<uint32_t> orient_pending;   // triangles the six-sample orientation test left open (one slot per raw triangle)
     DevBuf<float> ustart, upos, unrm;
     // Mesh outputs are double-buffered: while one mesh is being copied to the host on copy_stream (sdm_mesh_download_async)
     // the next remesh writes the other set.
@@ -298,10 +312,10 @@ struct SdmHandle {
     bool mesh_valid = false;
 
     // persistent grid sizes
-    int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_light = 0, g_edges = 0;
+    int g_refine = 0, g_classify = 0, g_project = 0, g_tail = 0, g_normals = 0, g_orient = 0, g_orient_quick = 0, g_orient_pending = 0, g_light = 0, g_edges = 0;
     uint32_t proj_chunk = 256;          // vertex chunk per warp in k_project (SDM_PROJ_CHUNK overrides)
     float slack_factor = 1.0f;         // inflation of the list regions in units of the child voxel size (SDM_SLACK overrides)
-    bool use_lists = true, use_lattice = true, use_masks = true;   // SDM_NO_LISTS / SDM_NO_LATTICE / SDM_NO_MASKS: developer switches (A/B measurements, tests)
+    bool use_lists = true, use_lattice = true, use_masks = true, use_quick_orient = true;   // SDM_NO_LISTS / SDM_NO_LATTICE / SDM_NO_MASKS: developer switches (A/B measurements, tests)
 
     SdmStats stats {};
 
@@ -372,7 +386,8 @@ int configure_kernels(SdmHandle* h) {
     const K ks[] = {
         { (const void*) k_refine, 256, &h->g_refine },   { (const void*) k_cases, 256, &h->g_classify },
         { (const void*) k_project, 128, &h->g_project }, { (const void*) k_vertex_normals, 128, &h->g_normals },
-        { (const void*) k_orient, 128, &h->g_orient },   { (const void*) k_project_tail, 128, &h->g_tail },
+        { (const void*) k_orient<false>, 128, &h->g_orient },   { (const void*) k_project_tail, 128, &h->g_tail },
+        { (const void*) k_orient<true>, 128, &h->g_orient_quick }, { (const void*) k_orient_pending, 128, &h->g_orient_pending },
     };
     for (const K& k : ks) {
         const size_t smem = smem_for(h, k.threads);
@@ -452,6 +467,7 @@ int reserve_all(SdmHandle* h, uint32_t cap_vox, uint32_t cap_tris, uint32_t cap_
     CK(h->first_bits.reserve(((size_t) cap_tris * 3 + 31) / 32 + 32));
     CK(h->first_prefix.reserve(((size_t) cap_tris * 3 + 31) / 32 + 32));
     CK(h->tri_valid_bits.reserve(((size_t) cap_tris + 31) / 32 + 32));
+    CK(h->orient_pending.reserve((size_t) cap_tris + 32));
     CK(h->tri_prefix.reserve(((size_t) cap_tris + 31) / 32 + 32));
     CK(h->first_slot.reserve(cap_uniq));
     CK(h->wref.reserve(cap_uniq));
@@ -659,8 +675,16 @@ int enqueue_mesh_local(SdmHandle* h, bool fuse_weld_keys) {
     }
     {
         NvtxRange nv(h, "mesh: orient");
-        k_orient<<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
-                                                    h->tri_valid_bits.p, h->grid, vl, h->tri_rec.p, h->uesc.p);
+        if (h->lipschitz && h->use_quick_orient) {
+            k_orient<true><<<h->g_orient_quick, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
+                                                              h->tri_valid_bits.p, h->grid, vl, h->tri_rec.p, h->uesc.p, h->orient_pending.p, h->scene_reach);
+            k_orient_pending<<<h->g_orient_pending, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p,
+                                                                       h->first_slot.p, h->tri_valid_bits.p, h->grid, vl, h->tri_rec.p, h->uesc.p, h->orient_pending.p);
+            h->stats.kernel_launches++;
+        } else {
+            k_orient<false><<<h->g_orient, 128, smem128, s>>>(h->scene.p, h->state.p, h->entry_uid.p, h->slot_ref.p, h->upos.p, h->tri_uid.p, h->first_slot.p,
+                                                               h->tri_valid_bits.p, h->grid, vl, h->tri_rec.p, h->uesc.p, nullptr, 0.0f);
+        }
         mark(h, "k_orient");
     }
     h->stats.kernel_launches += 6;
@@ -782,7 +806,8 @@ int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count) {
     if (!h || (!prims && count)) return fail(SDM_ERR_INVALID, "null argument");
     std::vector<uint4> blob;
     bool mb = false;
-    int rc = compile_scene(prims, count, blob, &mb);
+    float reach = 0.0f;
+    int rc = compile_scene(prims, count, blob, &mb, &reach);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));   // the previous table may still be in use
@@ -795,6 +820,8 @@ int sdm_set_scene(SdmHandle* h, const SdmPrimitive* prims, uint32_t count) {
     h->scene_nprims = reinterpret_cast<const SceneHeader*>(blob.data())->nprims;
     // culling pays off once the table is long; it needs 1-Lipschitz primitives (not the Mandelbulb estimator)
     h->mask_capable = !mb && h->scene_nprims > 24 && h->use_masks;
+    h->lipschitz = !mb;   // sphere / capsule / box folded by min / smooth-min: the six-sample orientation test applies
+    h->scene_reach = reach;
     h->grid.enabled = 0;   // masks depend on the scene: rebuilt on the next remesh
     h->mesh_valid = false;
     // shared-memory sizes / persistent grid sizes only depend on these three: an animated scene (same table shape every
@@ -838,6 +865,7 @@ int sdm_create(int device_ordinal, SdmHandle** out_handle) {
         if (const char* e = getenv("SDM_PROJ_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->proj_chunk = (uint32_t) v & ~31u; }
         h->use_lists = getenv("SDM_NO_LISTS") == nullptr;
         h->use_lattice = getenv("SDM_NO_LATTICE") == nullptr;
+        h->use_quick_orient = getenv("SDM_NO_QUICK_ORIENT") == nullptr;   // off: twelve evaluations for every triangle's orientation
         h->use_masks = getenv("SDM_NO_MASKS") == nullptr;   // off: every evaluation folds the whole table (the reference's own semantics)
         SdmPrimitive def[2];
         sdm_scene_default(def, 2);
@@ -859,7 +887,7 @@ void sdm_destroy(SdmHandle* h) {
     h->masks_fine.release(); h->masks_coarse.release(); h->cell_maybe.release();
     h->scene.release(); h->vox[0].release(); h->vox[1].release(); h->cases.release(); h->tri_off.release(); h->slot_ref.release();
     h->tri_uid.release(); h->first_slot.release(); h->wref.release(); h->first_bits.release(); h->first_prefix.release();
-    h->tri_valid_bits.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
+    h->tri_valid_bits.release(); h->orient_pending.release(); h->tri_prefix.release(); h->ustart.release(); h->upos.release(); h->unrm.release();
     for (int b = 0; b < 2; b++) { h->out_pos[b].release(); h->out_nrm[b].release(); h->out_idx[b].release(); }
     h->entry_uid.release(); h->vidx.release(); h->m27.release(); h->table1.release(); h->table2.release(); h->tiles.release();
     for (int i = 0; i < 2; i++) { h->vl[i].release(); h->vparent[i].release(); }

@@ -53,6 +53,7 @@ struct DevState {
     uint32_t peer_scan_total[2];   // totals of the peer exchange's bitmap scans (unused by the host)
     uint32_t n_escaped;         // vertices whose Newton iterate left the region their inherited list is proven for (general path)
     uint32_t list_fallbacks;    // tiles of the mesh stage that had to use the cell masks instead of inherited lists
+    uint32_t n_orient_pending;  // triangles whose orientation the six-sample test of k_orient<true> left open (k_orient_pending)
     unsigned long long prim_evals[6];   // (primitive, point) distance evaluations: refine, classify, project, tail, normals, orient
     unsigned long long newton_iters;   // total closest_surface_point iterations (statistics)
     unsigned long long tail_steps, tail_rebuilds, tail_unlisted;   // k_project_tail: warp steps, list rebuilds, steps without a tile list (sdm_debug_fetch "state")
@@ -636,7 +637,7 @@ __global__ void k_reset_mesh_state(DevState* st) {
     for (int i = TK_CLASSIFY; i < TK_COUNT; i++) st->ticket[i] = 0;
     st->n_stragglers = 0; st->weld_dups = 0;
     st->newton_iters = 0; st->tail_steps = 0; st->tail_rebuilds = 0; st->tail_unlisted = 0;
-    st->n_escaped = 0; st->list_fallbacks = 0;
+    st->n_escaped = 0; st->list_fallbacks = 0; st->n_orient_pending = 0;
     for (int i = WK_CLASSIFY; i < 6; i++) st->prim_evals[i] = 0;   // refine's counter is reset with the field
 }
 
@@ -972,11 +973,76 @@ __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint
 }
 
 // Per raw triangle: orientation test and the reference host's triangle filter.
+// One triangle's loads: vertex ids (pre-flip), positions, centroid (compute_mesh_generation.cu:104).
+struct OrientTri { uint32_t u[3]; float v[3][3]; float mx, my, mz; };
+__device__ __forceinline__ void orient_load(OrientTri& r, bool active, uint32_t t, const uint32_t* __restrict__ entry_uid, const uint32_t* __restrict__ slot_ref,
+                                            const float* __restrict__ upos) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) { r.u[j] = 0; r.v[j][0] = r.v[j][1] = r.v[j][2] = 0.f; }
+    r.mx = r.my = r.mz = 0.f;
+    if (!active) return;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        r.u[j] = entry_uid[slot_ref[3 * (size_t) t + j]];
+        r.v[j][0] = upos[3 * (size_t) r.u[j]]; r.v[j][1] = upos[3 * (size_t) r.u[j] + 1]; r.v[j][2] = upos[3 * (size_t) r.u[j] + 2];
+    }
+    // (v0 + v1 + v2) / 3.0f
+    r.mx = (r.v[0][0] + r.v[1][0] + r.v[2][0]) / 3.0f; r.my = (r.v[0][1] + r.v[1][1] + r.v[2][1]) / 3.0f; r.mz = (r.v[0][2] + r.v[1][2] + r.v[2][2]) / 3.0f;
+}
+// normalize(cross(v1 - v0, v2 - v0))   (compute_mesh_generation.cu:103)
+__device__ __forceinline__ void orient_face_normal(const OrientTri& r, float& tnx, float& tny, float& tnz) {
+    const float ax = r.v[1][0] - r.v[0][0], ay = r.v[1][1] - r.v[0][1], az = r.v[1][2] - r.v[0][2];
+    const float bx = r.v[2][0] - r.v[0][0], by = r.v[2][1] - r.v[0][1], bz = r.v[2][2] - r.v[0][2];
+    const float cx = ay * bz - by * az, cy = az * bx - bz * ax, cz = ax * by - bx * ay;
+    const float inv = 1.0f / sqrtf(dot3(cx, cy, cz, cx, cy, cz));
+    tnx = cx * inv; tny = cy * inv; tnz = cz * inv;
+}
+// the triangle's corner order after the flip (:105-113), the reference host's finite filter (src/cuda/mod.rs:289), first-occurrence slots
+__device__ __forceinline__ bool orient_store(const OrientTri& r, bool flip, uint32_t t, uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot) {
+    const uint32_t f0 = flip ? r.u[2] : r.u[0], f2 = flip ? r.u[0] : r.u[2];
+    const float first_x = flip ? r.v[2][0] : r.v[0][0];
+    tri_uid[3 * (size_t) t] = f0; tri_uid[3 * (size_t) t + 1] = r.u[1]; tri_uid[3 * (size_t) t + 2] = f2;
+    const bool valid = fabsf(first_x) <= FLT_MAX;   // kept iff vertices[0].position.x is finite
+    if (valid) {
+        atomicMin(first_slot + f0, 3u * t);
+        atomicMin(first_slot + r.u[1], 3u * t + 1u);
+        atomicMin(first_slot + f2, 3u * t + 2u);
+    }
+    return valid;
+}
+// The tile's primitive list for the centroids.  The centroid lies in the convex hull of the three vertices; each ended within `slack`
+// of its start point on this triangle's voxel (unless flagged), so the centroid is inside the region the voxel's list record is proven for.
+__device__ __forceinline__ bool orient_tile_list(const SceneView& sc, const MaskGrid& grid, bool lists, bool active, const OrientTri& r, uint32_t t,
+                                                 const uint4* __restrict__ vl, const uint32_t* __restrict__ tri_rec, const uint32_t* __restrict__ uesc, bool& esc) {
+    bool listed = false;
+    esc = false;
+    if (lists) {
+        if (active) esc = (((uesc[r.u[0] >> 5] >> (r.u[0] & 31u)) | (uesc[r.u[1] >> 5] >> (r.u[1] & 31u)) | (uesc[r.u[2] >> 5] >> (r.u[2] & 31u))) & 1u) != 0u;
+        if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, active, vl, active ? tri_rec[t] : 0u, r.mx, r.my, r.mz);
+    }
+    if (!listed) tile_mask_from_point(grid, sc, active, r.mx, r.my, r.mz);
+    return listed;
+}
+
+// QUICK = false: the reference's statement - twelve evaluations per triangle.
+// QUICK = true (scenes of 1-Lipschitz primitives: everything but the Mandelbulb estimator): only the SIGN of dot(tn, n) is used (:105),
+// n = normalize(d), d_axis = 8 A_axis - B_axis with A = f(+e) - f(-e), B = f(+2e) - f(-2e) (signed_distance.cu:186-199).  The exact
+// scene function is 1-Lipschitz, so |B_axis| <= 4e (+ what rounding adds) whatever the scene does between the samples, and
+//     8 |tn . A|  >  |tn|_1 * Bmax   ==>   sign(tn . d) = sign(tn . A):
+// six evaluations decide the triangle.  What rounding adds, all in the bound: the evaluated f differs from the exact fold by at most
+// (L + 6) * 2e-7 * V (L = folded primitives, V = largest distance magnitude <= |centroid|_1 + `reach`, the host's bound on
+// |centre| + extent over the table: a distance rounds to <= 6 units of 2e-7 V, and a smooth-min step is non-expansive in the max norm
+// and rounds its own operations to one unit); the sample points are 4e apart up to 1e-3 relative; the reference's own left-to-right
+// sum rounds to 4e-6 (max|f| + 1e-3); 7.9 instead of 8 covers this test's own arithmetic.  The margin left makes |cos(tn, n)| > 1e-3,
+// far above the rounding of the reference's normalize and dot.  Triangles the test leaves open (a NaN anywhere, a sliver whose normal
+// is more than ~60 degrees off the gradient, a vertex flagged as escaped) go to `pending`: k_orient_pending applies the full statement.
+template <bool QUICK>
 __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __restrict__ scene, DevState* st, const uint32_t* __restrict__ entry_uid,
                                                 const uint32_t* __restrict__ slot_ref, const float* __restrict__ upos,
                                                 uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
                                                 uint32_t* __restrict__ tri_valid_bits, MaskGrid grid,
-                                                const uint4* __restrict__ vl, const uint32_t* __restrict__ tri_rec, const uint32_t* __restrict__ uesc) {
+                                                const uint4* __restrict__ vl, const uint32_t* __restrict__ tri_rec, const uint32_t* __restrict__ uesc,
+                                                uint32_t* __restrict__ pending, float reach) {
     extern __shared__ uint4 smem[];
     const SceneView sc = stage_scene_masked(scene, smem, grid);
     const uint32_t T = st->n_tris_raw;
@@ -986,7 +1052,6 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
     const uint32_t lane = threadIdx.x & 31u;
     // warp-contiguous mapping so that one lane can write the 32 validity bits of a warp's triangles
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long work = 0;
     uint32_t group = tile_group((T + 31u) >> 5, warps_total);
     for (uint32_t g0 = 0, gk = group;; gk++) {   // dynamic, guided hand-out, see k_vertex_normals
@@ -1009,55 +1074,89 @@ __global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __re
             else if (lane == 3u && lists) prefetch_l1(tri_rec + t0 + 32u);
         }
 #endif
-        bool valid = false;
-        uint32_t u[3] = { 0, 0, 0 };
-        float v[3][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
-        float mx = 0.f, my = 0.f, mz = 0.f;
+        OrientTri r;
+        orient_load(r, t < T, t, entry_uid, slot_ref, upos);
+        bool esc;
+        const bool listed = orient_tile_list(sc, grid, lists, t < T, r, t, vl, tri_rec, uesc, esc);
+        fallbacks += (lists && !listed) ? 1u : 0u;
+        const uint32_t L = tile_prims(sc);
+        work += (unsigned long long) L * (QUICK ? 6u : 12u) * min(32u, T - t0);
+        bool valid = false, open = false;
         if (t < T) {
+            float tnx, tny, tnz;
+            orient_face_normal(r, tnx, tny, tnz);
+            if (QUICK) {
+                // the +e / -e samples of each axis, built as normal_points builds them
+                float px[6], py[6], pz[6], f[6];
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                u[j] = entry_uid[slot_ref[3 * (size_t) t + j]];
-                v[j][0] = upos[3 * (size_t) u[j]]; v[j][1] = upos[3 * (size_t) u[j] + 1]; v[j][2] = upos[3 * (size_t) u[j] + 2];
-            }
-            // (v0 + v1 + v2) / 3.0f   (compute_mesh_generation.cu:104)
-            mx = (v[0][0] + v[1][0] + v[2][0]) / 3.0f; my = (v[0][1] + v[1][1] + v[2][1]) / 3.0f; mz = (v[0][2] + v[1][2] + v[2][2]) / 3.0f;
-        }
-        // The centroid lies in the convex hull of the three vertices; each ended within `slack` of its start point on this
-        // triangle's voxel (unless flagged), so the centroid is inside the region the voxel's list record is proven for.
-        bool listed = false;
-        if (lists) {
-            bool esc = false;
-            if (t < T) esc = (((uesc[u[0] >> 5] >> (u[0] & 31u)) | (uesc[u[1] >> 5] >> (u[1] & 31u)) | (uesc[u[2] >> 5] >> (u[2] & 31u))) & 1u) != 0u;
-            if (!__any_sync(0xffffffffu, esc)) listed = tile_list_from_records(sc, t < T, vl, t < T ? tri_rec[t] : 0u, mx, my, mz);
-        }
-        if (!listed) { tile_mask_from_point(grid, sc, t < T, mx, my, mz); fallbacks += lists ? 1u : 0u; }
-        work += (unsigned long long) tile_prims(sc) * 12u * min(32u, T - t0);
-        if (t < T) {
-            // normalize(cross(v1 - v0, v2 - v0))   (:103)
-            const float ax = v[1][0] - v[0][0], ay = v[1][1] - v[0][1], az = v[1][2] - v[0][2];
-            const float bx = v[2][0] - v[0][0], by = v[2][1] - v[0][1], bz = v[2][2] - v[0][2];
-            const float cx = ay * bz - by * az, cy = az * bx - bz * ax, cz = ax * by - bx * ay;
-            const float inv = 1.0f / sqrtf(dot3(cx, cy, cz, cx, cy, cz));
-            const float tnx = cx * inv, tny = cy * inv, tnz = cz * inv;
-            float nx, ny, nz;
-            empirical_normal(sc, mx, my, mz, nx, ny, nz);   // empirical_normal(sd_obj, centroid)   (:104)
-            const bool flip = dot3(tnx, tny, tnz, nx, ny, nz) <= 0.0f;   // :105
-            const uint32_t f0 = flip ? u[2] : u[0], f2 = flip ? u[0] : u[2];
-            const float first_x = flip ? v[2][0] : v[0][0];
-            tri_uid[3 * (size_t) t] = f0; tri_uid[3 * (size_t) t + 1] = u[1]; tri_uid[3 * (size_t) t + 2] = f2;
-            // src/cuda/mod.rs:289: triangle kept iff vertices[0].position.x is finite
-            valid = fabsf(first_x) <= FLT_MAX;
-            if (valid) {
-                atomicMin(first_slot + f0, 3u * t);
-                atomicMin(first_slot + u[1], 3u * t + 1u);
-                atomicMin(first_slot + f2, 3u * t + 2u);
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const float o = q == 0 ? SDM_NORMAL_EPSILON : -SDM_NORMAL_EPSILON;
+                        px[2 * a + q] = r.mx + (a == 0 ? o : 0.0f); py[2 * a + q] = r.my + (a == 1 ? o : 0.0f); pz[2 * a + q] = r.mz + (a == 2 ? o : 0.0f);
+                    }
+                eval_scene<6>(sc, px, py, pz, f);
+                const float dotA = tnx * (f[0] - f[1]) + tny * (f[2] - f[3]) + tnz * (f[4] - f[5]);
+                const float l1 = fabsf(tnx) + fabsf(tny) + fabsf(tnz);
+                const float fmax = fmaxf(fmaxf(fmaxf(fabsf(f[0]), fabsf(f[1])), fmaxf(fabsf(f[2]), fabsf(f[3]))), fmaxf(fabsf(f[4]), fabsf(f[5])));
+                const float unit = 2e-7f * (reach + fabsf(r.mx) + fabsf(r.my) + fabsf(r.mz));
+                const float bmax = 4.0f * SDM_NORMAL_EPSILON * 1.003f + 2.0f * (float) (L + 6u) * unit + 4e-6f * (fmax + 1e-3f);
+                if (!esc && 7.9f * fabsf(dotA) > l1 * bmax) valid = orient_store(r, dotA < 0.0f, t, tri_uid, first_slot);   // false for any NaN / inf
+                else open = true;
+            } else {
+                float nx, ny, nz;
+                empirical_normal(sc, r.mx, r.my, r.mz, nx, ny, nz);   // empirical_normal(sd_obj, centroid)   (:104)
+                valid = orient_store(r, dot3(tnx, tny, tnz, nx, ny, nz) <= 0.0f, t, tri_uid, first_slot);   // :105
             }
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, valid);
         if (lane == 0) tri_valid_bits[t0 >> 5] = bits;
+        if (QUICK) {
+            const uint32_t ob = __ballot_sync(0xffffffffu, open);
+            if (ob) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&st->n_orient_pending, (uint32_t) __popc(ob));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (open) pending[base + __popc(ob & ((1u << lane) - 1u))] = t;   // capacity: one slot per raw triangle
+            }
+        }
     }
     if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_ORIENT], work);
     if (lane == 0 && fallbacks) atomicAdd(&st->list_fallbacks, fallbacks);
+}
+
+// The triangles k_orient<true> left open: the reference's full statement.  Their validity bits are OR-ed into the words k_orient wrote.
+__global__ void __launch_bounds__(128) k_orient_pending(const uint4* __restrict__ scene, DevState* st, const uint32_t* __restrict__ entry_uid,
+                                                        const uint32_t* __restrict__ slot_ref, const float* __restrict__ upos,
+                                                        uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
+                                                        uint32_t* __restrict__ tri_valid_bits, MaskGrid grid,
+                                                        const uint4* __restrict__ vl, const uint32_t* __restrict__ tri_rec, const uint32_t* __restrict__ uesc,
+                                                        const uint32_t* __restrict__ pending) {
+    extern __shared__ uint4 smem[];
+    const SceneView sc = stage_scene_masked(scene, smem, grid);
+    const uint32_t n = min(st->n_orient_pending, st->n_tris_raw);
+    if (st->error_flags) return;
+    const bool lists = vl != nullptr && sc.wmask != nullptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long work = 0;
+    for (uint32_t i0 = warp_id * 32u; i0 < n; i0 += warps_total * 32u) {
+        const bool active = i0 + lane < n;
+        const uint32_t t = active ? pending[i0 + lane] : 0u;
+        OrientTri r;
+        orient_load(r, active, t, entry_uid, slot_ref, upos);
+        bool esc;
+        orient_tile_list(sc, grid, lists, active, r, t, vl, tri_rec, uesc, esc);
+        work += (unsigned long long) tile_prims(sc) * 12u * min(32u, n - i0);
+        if (active) {
+            float tnx, tny, tnz, nx, ny, nz;
+            orient_face_normal(r, tnx, tny, tnz);
+            empirical_normal(sc, r.mx, r.my, r.mz, nx, ny, nz);
+            if (orient_store(r, dot3(tnx, tny, tnz, nx, ny, nz) <= 0.0f, t, tri_uid, first_slot)) atomicOr(tri_valid_bits + (t >> 5), 1u << (t & 31u));
+        }
+    }
+    if (lane == 0 && work) atomicAdd(&st->prim_evals[WK_ORIENT], work);
 }
 
 // The reference-order weld (src/cuda/mod.rs:263-296).  A vertex's key entry is created by weld_insert_key (fused into

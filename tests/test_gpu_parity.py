@@ -214,11 +214,12 @@ def test_fullsize_matches_reference_goldens(handler, oracle_mod, case, init, lev
     assert h(mesh.normals) == want["fnv_normals"], "vertex normals differ"
 
 
-@pytest.mark.parametrize("switch", ["SDM_NO_LISTS", "SDM_NO_LATTICE", "SDM_SLACK=0.25"])
+@pytest.mark.parametrize("switch", ["SDM_NO_LISTS", "SDM_NO_LATTICE", "SDM_SLACK=0.25", "SDM_NO_QUICK_ORIENT"])
 def test_fallback_paths_give_the_same_mesh(handler, switch, monkeypatch):
-    """The fast paths (inherited primitive lists, 64-bit lattice vertex keys) each have a general path
-    behind them (cell masks, float-bit keys) that also serves whatever the fast path cannot take; a small slack
-    sends many Newton iterates through the hand-over to the tail kernel.  All of them must produce the same bytes."""
+    """The fast paths (inherited primitive lists, 64-bit lattice vertex keys, the six-sample orientation test) each have a
+    general path behind them (cell masks, float-bit keys, the reference's twelve-sample statement) that also serves whatever the
+    fast path cannot take; a small slack sends many Newton iterates through the hand-over to the tail kernel.  All of them
+    must produce the same bytes."""
     scene = scenes.many_primitives(256)
     handler.set_scene(scene)
     want = handler.remesh(5.0, 32, 3)
