@@ -1745,6 +1745,16 @@ int sdm_peer_root_export(SdmHandle* h, uint32_t world, uint32_t cap_rows, SdmPee
     if (world == 0 || world > SDM_PEER_MAX || cap_rows == 0) return fail(SDM_ERR_INVALID, "1..32 ranks, cap_rows > 0");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    // The resolve step (P2 of sdm_peer_step) keeps one word per key row in this handle's per-vertex scratch and the rows' keys in its
+    // vertex table: world x cap_rows rows must fit (2 vertices per voxel of capacity; the table has 2 entries per vertex).  Growing here,
+    // before the output buffers are exported, instead of failing at the first step.
+    if ((uint64_t) world * cap_rows > h->cap_uniq) {
+        uint32_t want = 0;
+        int rc = capacity_for(h, ((uint64_t) world * cap_rows + 1) / 2, &want);
+        if (rc) return rc;
+        rc = ensure_capacity(h, want);
+        if (rc) return rc;
+    }
     const size_t bytes = peer_block_bytes(world, cap_rows);
     CK(h->peer_block.reserve(bytes));
     CK(cudaMemset(h->peer_block.p, 0, bytes));
