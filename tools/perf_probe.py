@@ -19,6 +19,7 @@ def run(name, scene, bb, init, levels, reps=3):
     pe = st["prim_evals"]; lc = st["level_counts"]
     ev = dict(refine=27 * sum(lc[:levels]), classify=8 * lc[levels], normals=12 * st["unique_vertices"], orient=12 * st["raw_triangles"])
     ev["project"] = st["sdf_evals"] - sum(ev.values())
+    # (orient: 12 per triangle as the algorithm states it; the six-sample test really evaluates about half of them)
     print("     primitives folded per evaluation: " + ", ".join(f"{k} {pe[k] / max(v, 1):.1f}" for k, v in ev.items()))
     for k, ms in h.kernel_times():
         print(f"     {k:18s} {ms*1e3:9.1f} us")
