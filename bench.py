@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)   # an nvidia-smi query takes ~40 ms itself; the default timed region is ~0.2 s
 
     def stop(self):
         self._halt.set()
