@@ -230,13 +230,14 @@ __device__ __forceinline__ uint32_t refine_keep_mask(uint32_t m27) {
     }
     return keep;
 }
-// one parent per thread: a warp's children land in one contiguous run (4 parents per thread made the stores strided: slower)
+// one parent per thread: a warp's children land in one contiguous run, which the warp writes together
 __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ in_vox, float* __restrict__ out_vox, DevState* st, int level,
                                                      uint32_t epoch, uint64_t* tiles, uint32_t cap_vox, float osx, float osy, float osz,
                                                      const uint32_t* __restrict__ in_m27, uint8_t* __restrict__ out_cases,
                                                      uint32_t* __restrict__ vparent_out /* record index (= parent) per child, or null */) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_w[10];
+    __shared__ uint8_t s_desc[8][256];   // per warp: (owner lane << 3 | child) of every output slot of the warp's run
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = st->level_count[level];
     const uint32_t ntiles = (n + blockDim.x - 1u) / blockDim.x;
@@ -266,15 +267,37 @@ __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ i
         const uint32_t base = block_lookback(tiles, tile, epoch, total, s_w, block_end);
         if (block_end > cap_vox) {
             if (threadIdx.x == 0) atomicOr(&st->error_flags, ERR_VOXEL_CAP);
-        } else if (keep) {
-            const float bx = in_vox[3 * (size_t) p + 0], by = in_vox[3 * (size_t) p + 1], bz = in_vox[3 * (size_t) p + 2];
-            uint32_t pos = base + incl - cnt;
+        } else if (total) {
+            // A warp's children are one contiguous run of the output, [base, base + total).  Written thread by thread (each parent its
+            // own <= 8 children) every store instruction touched up to 32 sectors; here the run is written by the warp: a descriptor
+            // (owner lane, child) per output slot in shared memory, then 32 slots at a time - the parent's base through a shuffle,
+            // the same float expression for the child, and the 96 floats of 32 children as three fully coalesced stores.
+            uint8_t* desc = s_desc[threadIdx.x >> 5];
+            {
+                uint32_t o = incl - cnt;
 #pragma unroll
-            for (int ch = 0; ch < 8; ch++) {
-                if (keep & (1u << ch)) {
-                    out_vox[3 * (size_t) pos + 0] = bx + (float) (ch >> 2) * osx;
-                    out_vox[3 * (size_t) pos + 1] = by + (float) ((ch >> 1) & 1) * osy;
-                    out_vox[3 * (size_t) pos + 2] = bz + (float) (ch & 1) * osz;
+                for (int ch = 0; ch < 8; ch++)
+                    if (keep & (1u << ch)) desc[o++] = (uint8_t) ((lane << 3) | (uint32_t) ch);
+            }
+            __syncwarp();
+            float bx = 0.f, by = 0.f, bz = 0.f;
+            if (keep) { bx = in_vox[3 * (size_t) p + 0]; by = in_vox[3 * (size_t) p + 1]; bz = in_vox[3 * (size_t) p + 2]; }
+            for (uint32_t k0 = 0; k0 < total; k0 += 32u) {
+                const uint32_t k = k0 + lane;
+                const bool valid = k < total;
+                const uint32_t d = valid ? desc[k] : 0u, owner = d >> 3;
+                const int ch = (int) (d & 7u);
+                const float obx = __shfl_sync(0xffffffffu, bx, owner), oby = __shfl_sync(0xffffffffu, by, owner), obz = __shfl_sync(0xffffffffu, bz, owner);
+                const uint32_t om27 = __shfl_sync(0xffffffffu, m27, owner);
+                const float x = obx + (float) (ch >> 2) * osx, y = oby + (float) ((ch >> 1) & 1) * osy, z = obz + (float) (ch & 1) * osz;
+                float* run = out_vox + 3 * (size_t) (base + k0);
+#pragma unroll
+                for (uint32_t i = 0; i < 3u; i++) {
+                    const uint32_t f = 32u * i + lane, c = f / 3u, comp = f - 3u * c;
+                    const float vx = __shfl_sync(0xffffffffu, x, c), vy = __shfl_sync(0xffffffffu, y, c), vz = __shfl_sync(0xffffffffu, z, c);
+                    if (k0 + c < total) run[f] = comp == 0u ? vx : (comp == 1u ? vy : vz);
+                }
+                if (valid) {
                     if (out_cases) {
                         // cube_index bit c = sign at corner c: +x iff c%4 in {1,2}, +y iff c%4 >= 2, +z iff c >= 4
                         uint32_t cube = 0;
@@ -282,14 +305,14 @@ __global__ void __launch_bounds__(256) k_refine_emit(const float* __restrict__ i
                         for (int c = 0; c < 8; c++) {
                             const int dx = ((c & 3) == 1 || (c & 3) == 2) ? 1 : 0, dy = ((c & 3) >= 2) ? 1 : 0, dz = (c >= 4) ? 1 : 0;
                             const int l = ((ch >> 2) + dx) * 9 + (((ch >> 1) & 1) + dy) * 3 + ((ch & 1) + dz);
-                            cube |= ((m27 >> l) & 1u) << c;
+                            cube |= ((om27 >> l) & 1u) << c;
                         }
-                        out_cases[pos] = (uint8_t) cube;
+                        out_cases[base + k] = (uint8_t) cube;
                     }
-                    if (vparent_out) vparent_out[pos] = p;
-                    pos++;
+                    if (vparent_out) vparent_out[base + k] = p - lane + owner;
                 }
             }
+            __syncwarp();   // the descriptors are rewritten by the next tile
         }
         if (tile == ntiles - 1 && threadIdx.x == 0) st->level_count[level + 1] = min(block_end, cap_vox);
     }
