@@ -105,3 +105,15 @@ def test_kept_primitives_fold_to_the_same_bits(oracle_mod, nprims, rho):
         part = oracle_mod.Oracle(sub).sdf(pts)
         assert np.array_equal(full.view(np.uint32), part.view(np.uint32)), f"ball {b}: kept list of {sub.shape[0]} differs from the whole table"
     assert np.mean(kept_sizes) < 40, "the rule should cull most of the primitives"
+
+
+@pytest.mark.parametrize("scene_name", ["many256", "sd_obj", "sphere_box"])
+def test_a_nan_point_folds_to_the_start_value_whatever_is_folded(oracle_mod, scene_name):
+    """tile_mask_from_point / tile_mask_from_half_points give a point with a NaN coordinate an EMPTY list: every sphere / capsule /
+    box distance at it is NaN and the fold skips NaN distances, so the whole table returns the fold's start value (FLT_MAX) too."""
+    table = {"many256": lambda: scenes.many_primitives(256), "sd_obj": scenes.sd_obj, "sphere_box": scenes.sphere_box}[scene_name]()
+    pts = np.array([[np.nan, 0, 0], [0.3, np.nan, 1.0], [np.nan] * 3, [1.0, 2.0, np.nan], [np.nan, np.inf, 0.0]], F)
+    want = np.full(pts.shape[0], np.finfo(F).max, F)
+    assert np.array_equal(oracle_mod.Oracle(table).sdf(pts).view(np.uint32), want.view(np.uint32))
+    for i in range(0, table.shape[0], max(1, table.shape[0] // 16)):      # ... and so does every single primitive
+        assert np.array_equal(oracle_mod.Oracle(table[i:i + 1]).sdf(pts).view(np.uint32), want.view(np.uint32))
