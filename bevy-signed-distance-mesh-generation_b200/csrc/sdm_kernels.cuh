@@ -934,7 +934,7 @@ __device__ __forceinline__ uint32_t weld_insert_key(DevState* st, const float* _
 // DRAM access per vertex that is free while the SM is busy with the twelve evaluations (as a kernel of its own it took a
 // third of this kernel's time doing nothing but waiting for memory).
 #ifndef SDM_NRM_MINB
-#define SDM_NRM_MINB 5   /* 96 registers: 1.35 -> 1.22 ms on configs[2] (6 blocks = 80 registers spilled the per-lane test's state) */
+#define SDM_NRM_MINB 6   /* 80 registers, no spills since the per-lane test takes one candidate per step: 1.24 -> 1.16 ms on configs[2] (96 registers / 5 blocks was the better choice while that test was unrolled by two) */
 #endif
 __global__ void __launch_bounds__(128, SDM_NRM_MINB) k_vertex_normals(const uint4* __restrict__ scene, DevState* st, const float* __restrict__ upos,
                                                         float* __restrict__ unrm, uint32_t cap_uniq, MaskGrid grid, uint4* weld_table,
