@@ -1059,8 +1059,11 @@ __device__ __forceinline__ bool orient_tile_list(const SceneView& sc, const Mask
 // sum rounds to 4e-6 (max|f| + 1e-3); 7.9 instead of 8 covers this test's own arithmetic.  The margin left makes |cos(tn, n)| > 1e-3,
 // far above the rounding of the reference's normalize and dot.  Triangles the test leaves open (a NaN anywhere, a sliver whose normal
 // is more than ~60 degrees off the gradient, a vertex flagged as escaped) go to `pending`: k_orient_pending applies the full statement.
+#ifndef SDM_ORIENT_MINB
+#define SDM_ORIENT_MINB 6   /* 80 registers (20 bytes spilled): 1.385 -> 1.315 ms on configs[2]; the six-sample pass needs fewer registers than k_project's 13 points */
+#endif
 template <bool QUICK>
-__global__ void __launch_bounds__(128, SDM_PROJ_MINB) k_orient(const uint4* __restrict__ scene, DevState* st, const uint32_t* __restrict__ entry_uid,
+__global__ void __launch_bounds__(128, SDM_ORIENT_MINB) k_orient(const uint4* __restrict__ scene, DevState* st, const uint32_t* __restrict__ entry_uid,
                                                 const uint32_t* __restrict__ slot_ref, const float* __restrict__ upos,
                                                 uint32_t* __restrict__ tri_uid, uint32_t* __restrict__ first_slot,
                                                 uint32_t* __restrict__ tri_valid_bits, MaskGrid grid,
