@@ -697,7 +697,8 @@ __global__ void __launch_bounds__(256) k_clear_weld_state(DevState* st, uint32_t
 struct Straggler { uint32_t uid, it; float g[3]; float s[3]; uint32_t power, lam, stop_at, pad; };   // 48 B: vertex, iterate, Brent state
 
 // 5 blocks of 128 threads per SM = 96 registers per thread: no spills, and 20 instead of 16 resident warps hide the low-ILP
-// stretches (per-lane culling, Newton update) - measured 12 % faster than the unconstrained 128-register build
+// stretches (per-lane culling, Newton update) - measured 12 % faster than the unconstrained 128-register build; 6 blocks (80
+// registers, 36 bytes spilled) is slower again: 3.15 -> 3.24 ms on configs[2]
 #ifndef SDM_PROJ_MINB
 #define SDM_PROJ_MINB 5
 #endif
